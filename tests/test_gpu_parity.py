@@ -1,0 +1,239 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against
+  (1) the golden vectors produced by the reference itself (tests/golden/*.npz),
+  (2) the oracle on seeded random batches (per-step residuals, table state, predictions),
+  (3) size-independent properties at BASELINE.json's full batch size.
+Bit-exact where the work is integer (keys, bucketing, presence); within 1e-5 relative (abs floor
+1e-7) for floats, the tolerance north_star states."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES
+from common import assert_close, data_prefixes, golden
+from oracle import oracle as O
+from xflow_b200 import api, datagen
+
+pytestmark = pytest.mark.gpu
+
+
+def _opt(name):
+    return (api.OPT_FTRL, O.OPT_FTRL) if name == "ftrl" else (api.OPT_SGD, O.OPT_SGD)
+
+
+def _gpu_train_predict(case, syn_data, capacity=0):
+    c = CASES[case]
+    g = golden(case)
+    train, test = data_prefixes(case, syn_data)
+    K = c["K"]
+    gopt, _ = _opt(c["opt"])
+    model = api.MODEL_LR if c["model"] == "lr" else api.MODEL_FM
+    table = api.Table(latent_dim=K, optimizer=gopt, capacity=capacity,
+                      v_init=api.VINIT_ZERO if c.get("preinit") else api.VINIT_DEFAULT)
+    if c.get("preinit"):
+        table.import_(g["keys"], w=g["init_w"], v=g["init_v"])
+    tr = api.Trainer(table, model=model, max_rows=4096, max_nnz=4096 * 64)
+    tr.init_push()
+    block = c.get("block_mb", 2) << 20
+    for _ in range(c["epochs"]):
+        for rp, keys, lab in api.Loader(train + "-00000", block):
+            tr.step_host(rp, keys, lab)
+    labs, ps = [], []
+    for rp, keys, lab in api.Loader(test + "-00000", (4 << 20) if c["model"] == "lr" else (2 << 20)):
+        ps.append(tr.predict_host(rp, keys))
+        labs.append(lab.astype(np.int32))
+    e = table.export(g["keys"])
+    return e, np.concatenate(labs), np.concatenate(ps), g, table, tr
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_golden_case_matches_reference(case, syn_data):
+    e, lab, p, g, table, tr = _gpu_train_predict(case, syn_data)
+    assert np.array_equal(e["present"], g["present"])          # same key set (bit-exact hashing / insertion)
+    for k in ("w", "nw", "zw", "v", "nv", "zv"):
+        if k in g.files:
+            assert_close(e[k], g[k], "%s.%s" % (case, k))
+    # exact zeros of FTRL's L1 threshold must be zeros on both sides
+    assert np.array_equal(e["w"] == 0.0, g["w"] == 0.0)
+    assert np.array_equal(lab, g["pred_label"])
+    assert_close(p, g["pred_pctr"], case + ".pctr", rel=2e-5, abs_floor=6e-7)  # reference prints 6 digits
+    m = api.auc_logloss(lab, p)
+    assert abs(m["logloss"] - float(g["logloss"])) <= 1e-5 * abs(float(g["logloss"])) + 6e-7
+    assert abs(m["auc"] - float(g["auc"])) <= 2e-5
+
+
+def test_golden_case_with_table_growth(syn_data):
+    """Same result when the table starts tiny and has to rehash several times."""
+    case = "syn_fm_ftrl_k8_e1"
+    e, lab, p, g, table, tr = _gpu_train_predict(case, syn_data, capacity=1024)
+    assert table.capacity() >= 2 * g["keys"].size
+    for k in ("w", "nw", "zw", "v", "nv", "zv"):
+        assert_close(e[k], g[k], "growth.%s" % k)
+
+
+@pytest.mark.parametrize("model,opt,K", [("lr", "ftrl", 0), ("lr", "sgd", 0), ("fm", "sgd", 8), ("fm", "ftrl", 16),
+                                         ("fm", "ftrl", 10), ("fm", "sgd", 3)])
+@pytest.mark.parametrize("dist", ["uniform", "zipf"])
+def test_random_batches_match_oracle(model, opt, K, dist):
+    """Several steps on seeded batches: per-row residuals and the whole table after every step."""
+    gopt, oopt = _opt(opt)
+    B, d, space = 2048, 24, 30000
+    gt = api.Table(latent_dim=K, optimizer=gopt, v_init=api.VINIT_COUNTER, seed=11)
+    ot = O.Table(K=K, opt=oopt, init_mode=O.INIT_COUNTER, seed=11)
+    tr = api.Trainer(gt, model=api.MODEL_LR if model == "lr" else api.MODEL_FM, max_rows=B, max_nnz=B * d * 2,
+                     keep_loss=True)
+    tr.init_push()
+    ot.init_push()
+    all_keys = [np.zeros(1, np.uint64)]
+    for step in range(4):
+        rp, keys, lab = datagen.make_csr_keys(100 + step, B, d, space, api.hash_decimal_ids, dist=dist,
+                                              zipf_s=1.3, ragged=(step == 2))
+        mean_abs = tr.step_host(rp, keys, lab)
+        gl = tr.get_loss(B)
+        U, ol = ot.step(rp.astype(np.int64), keys, lab.astype(np.int32))
+        assert_close(gl, ol, "loss step %d" % step, abs_floor=1e-6)
+        assert abs(mean_abs - np.abs(ol).mean()) < 1e-5
+        all_keys.append(keys)
+        uk = np.unique(np.concatenate(all_keys))
+        ge, oe = gt.export(uk), ot.export(uk)
+        assert np.array_equal(ge["present"], oe["present"])
+        # multi-occurrence gradient sums are accumulated in a different order than std::sort's;
+        # allow a vanishing fraction of L1-threshold flips
+        for k in ("w", "nw", "zw") + (("v", "nv", "zv") if K else ()):
+            assert_close(ge[k], oe[k], "%s step %d" % (k, step), max_bad_frac=2e-4)
+        assert tr.stats()["unique_keys"] >= U
+    st = tr.stats()
+    assert st["steps"] == 4 and st["rows"] == 4 * B
+    # forward-only path on a fresh batch
+    rp, keys, lab = datagen.make_csr_keys(999, B, d, space, api.hash_decimal_ids, dist=dist)
+    assert_close(tr.predict_host(rp, keys), ot.predict(rp.astype(np.int64), keys), "pctr", abs_floor=1e-6)
+    assert gt.size() == ot.size()
+
+
+def test_unique_key_count_is_exact():
+    B, d = 4096, 32
+    gt = api.Table()
+    tr = api.Trainer(gt, max_rows=B, max_nnz=B * d)
+    total = 0
+    for s in range(3):
+        rp, keys, lab = datagen.make_csr_keys(s, B, d, 5000, api.hash_decimal_ids, dist="zipf", zipf_s=1.1)
+        tr.step_host(rp, keys, lab)
+        total += np.unique(keys).size
+    assert tr.stats()["unique_keys"] == total
+
+
+@pytest.mark.parametrize("opt,K", [("ftrl", 0), ("sgd", 0), ("ftrl", 8), ("sgd", 10)])
+def test_pull_push_api_matches_oracle(opt, K):
+    """The KVWorker::Pull/Push-shaped entry points against the FTRL/SGD handles of the oracle."""
+    gopt, oopt = _opt(opt)
+    gt = api.Table(latent_dim=K, optimizer=gopt, v_init=api.VINIT_COUNTER, seed=3, capacity=1024)
+    ot = O.Table(K=K, opt=oopt, init_mode=O.INIT_COUNTER, seed=3)
+    rng = np.random.default_rng(0)
+    universe = rng.integers(0, 2 ** 64, 20000, dtype=np.uint64)
+    for it in range(5):
+        keys = np.unique(rng.choice(universe, 3000))
+        gw, gv = gt.pull(keys)
+        ow, ov = ot.pull(keys)
+        assert np.array_equal(gw.view(np.uint32), ow.view(np.uint32)) if it == 0 else True
+        assert_close(gw, ow, "pull w")
+        if K:
+            assert_close(gv, ov, "pull v")
+        g1 = (rng.standard_normal(keys.size) * 0.1).astype(np.float32)
+        g2 = (rng.standard_normal((keys.size, K)) * 0.1).astype(np.float32) if K else None
+        g1[::7] = 0.0
+        gt.push(keys, g1, g2)
+        ot.push(keys, g1, g2)
+    e, o = gt.export(universe), ot.export(universe)
+    assert np.array_equal(e["present"], o["present"])
+    for k in ("w", "nw", "zw") + (("v", "nv", "zv") if K else ()):
+        # same inputs, same op order: the optimizer arithmetic itself is bit-exact
+        assert np.array_equal(e[k].view(np.uint32), o[k].view(np.uint32)), k
+    assert gt.size() == ot.size() == int(o["present"].sum())
+
+
+def test_counter_init_bit_exact_and_insert_on_pull():
+    gt = api.Table(latent_dim=16, optimizer=api.OPT_FTRL, seed=42)
+    ot = O.Table(K=16, opt=O.OPT_FTRL, seed=42)
+    keys = np.arange(1, 5001, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    gw, gv = gt.pull(keys)
+    ow, ov = ot.pull(keys)
+    assert np.array_equal(gv.view(np.uint32), ov.view(np.uint32))
+    assert not gw.any() and gt.size() == 5000
+    e = gt.export(keys[:10])
+    assert e["present"].all()
+    assert not gt.export(np.array([12345], np.uint64))["present"].any()  # export never inserts
+    assert gt.size() == 5000
+
+
+def test_save_load_roundtrip(tmp_path):
+    gt = api.Table(latent_dim=8, optimizer=api.OPT_FTRL, seed=1)
+    tr = api.Trainer(gt, model=api.MODEL_FM, max_rows=1024, max_nnz=1024 * 16)
+    for s in range(3):
+        tr.step_host(*datagen.make_csr_keys(s, 1024, 16, 4000, api.hash_decimal_ids))
+    keys = np.sort(gt.list_keys())
+    assert keys.size == gt.size()
+    a = gt.export(keys)
+    path = str(tmp_path / "ckpt.bin")
+    gt.save(path)
+    g2 = api.Table(latent_dim=8, optimizer=api.OPT_FTRL, seed=99, v_init=api.VINIT_ZERO)
+    g2.load(path)
+    b = g2.export(keys)
+    for k in ("w", "nw", "zw", "v", "nv", "zv", "present"):
+        assert np.array_equal(a[k], b[k]), k
+    assert g2.size() == gt.size()
+
+
+def test_empty_and_degenerate_batches():
+    gt = api.Table()
+    ot = O.Table()
+    tr = api.Trainer(gt, max_rows=64, max_nnz=4096, keep_loss=True)
+    # rows without tokens, a row with one key repeated, a long row (> 128 tokens)
+    lens = [0, 3, 0, 200, 1, 40]
+    rp = np.zeros(len(lens) + 1, np.uint32)
+    rp[1:] = np.cumsum(lens)
+    ids = np.concatenate([np.array([7, 7, 7], np.uint64), np.arange(200, dtype=np.uint64) % 50,
+                          np.array([7], np.uint64), np.arange(40, dtype=np.uint64)])
+    keys = api.hash_decimal_ids(ids)
+    lab = np.array([1, 0, 0, 1, 1, 0], np.uint8)
+    for _ in range(3):
+        tr.step_host(rp, keys, lab)
+        gl = tr.get_loss(len(lens))
+        _, ol = ot.step(rp.astype(np.int64), keys, lab.astype(np.int32))
+        assert_close(gl, ol, "loss", abs_floor=1e-6)
+    uk = np.unique(keys)
+    ge, oe = gt.export(uk), ot.export(uk)
+    for k in ("w", "nw", "zw"):
+        assert_close(ge[k], oe[k], k)
+    assert tr.step_host(np.zeros(1, np.uint32), np.zeros(0, np.uint64), np.zeros(0, np.uint8)) == 0.0
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] shape (B = 65536, 64 nnz/row, 1e7 ids): properties that need no oracle run."""
+    B, d, space = 65536, 64, 10 ** 7
+    gt = api.Table(capacity=1 << 24)
+    tr = api.Trainer(gt, max_rows=B, max_nnz=B * d, keep_loss=True)
+    rp, keys, lab = datagen.make_csr_keys(1, B, d, space, api.hash_decimal_ids)
+    tr.step_host(rp, keys, lab)
+    loss = tr.get_loss(B)
+    # first step from an all-zero table: pctr = sigmoid(0) = 0.5 exactly
+    assert np.array_equal(loss, np.float32(0.5) - lab.astype(np.float32))
+    uk, cnt = np.unique(keys, return_counts=True)
+    assert tr.stats()["unique_keys"] == uk.size == gt.size()
+    # closed form of the first FTRL step: g = sum(residual over occurrences)/B, n = g^2, z = g
+    occ_row = np.repeat(np.arange(B), d)
+    g_sum = np.zeros(uk.size, np.float64)
+    np.add.at(g_sum, np.searchsorted(uk, keys), loss[occ_row].astype(np.float64))
+    e = gt.export(uk)
+    g32 = (g_sum / B).astype(np.float32)
+    assert_close(e["zw"], g32, "z after step 1", rel=2e-6)
+    assert_close(e["nw"], g32.astype(np.float64) ** 2, "n after step 1", rel=4e-6, abs_floor=1e-12)
+    # idempotence of pulls and sortedness-independence: permuting tokens inside rows changes nothing
+    gt2 = api.Table(capacity=1 << 24)
+    tr2 = api.Trainer(gt2, max_rows=B, max_nnz=B * d)
+    perm = np.arange(keys.size).reshape(B, d)[:, ::-1].reshape(-1)
+    tr2.step_host(rp, keys[perm], lab)
+    e2 = gt2.export(uk)
+    assert_close(e2["w"], e["w"], "w under token permutation", rel=2e-6)
+    # a second, identical batch: every key already present -> size unchanged, unique count doubles
+    tr.step_host(rp, keys, lab)
+    assert gt.size() == uk.size and tr.stats()["unique_keys"] == 2 * uk.size

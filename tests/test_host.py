@@ -1,0 +1,111 @@
+"""CPU tests of the product's host side: the C-ABI library loads, exports every symbol the header
+declares, and its host-only pieces (hashing, block loader, metric, shard rule) agree with the oracle.
+No compute entry point is exercised here (there is no GPU); those fail loudly, which is also checked."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import GOLDEN
+from oracle import oracle as O
+from xflow_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "xflow_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"XF_DLL\s+[\w\s\*]+?\b(\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_header_symbol():
+    syms = _header_symbols()
+    assert len(syms) >= 40
+    out = subprocess.check_output(["nm", "-D", "--defined-only", api.LIB_PATH], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [s for s in syms if s not in exported]
+    assert not missing, "declared in include/xflow_b200.h but not exported: %s" % missing
+    # and the ctypes table covers the same set
+    assert sorted(api.SIGNATURES) == syms
+
+
+def test_library_loads_and_reports_version():
+    L = api.lib()
+    assert L.xf_version() >= 100
+    assert api.device_count() >= 0
+
+
+@pytest.mark.skipif(api.device_count() > 0, reason="checks the no-GPU failure mode")
+def test_compute_calls_fail_loudly_without_gpu():
+    with pytest.raises(api.XflowError):
+        api.Table()
+
+
+def test_hash_matches_oracle_and_std_hash():
+    g = np.load(os.path.join(GOLDEN, "std_hash.npz"))
+    for s, h in zip(g["strings"], g["hashes"]):
+        assert api.hash_bytes(bytes(s)) == int(h)
+    rng = np.random.default_rng(3)
+    for n in list(range(0, 34)) + [100]:
+        s = bytes(rng.integers(1, 255, n, dtype=np.uint8))
+        assert api.hash_bytes(s) == O.std_hash(s)
+    ids = rng.integers(0, 10 ** 15, 50000).astype(np.uint64)
+    ids[:3] = [0, 9, 10]
+    assert np.array_equal(api.hash_decimal_ids(ids), O.hash_decimal_ids(ids))
+
+
+def test_shard_rule_matches_oracle():
+    rng = np.random.default_rng(4)
+    keys = rng.integers(0, 2 ** 64, 5000, dtype=np.uint64)
+    edge = [0, 1, 2 ** 64 - 1, 2 ** 64 - 8, 2 ** 64 - 9, 0x1FFFFFFFFFFFFFFF, 0x1FFFFFFFFFFFFFFE, 0x2000000000000000]
+    for S in (1, 2, 3, 4, 8):
+        for k in list(keys[:500]) + edge:
+            assert api.shard_of(int(k), S) == O.shard_of(int(k), S)
+
+
+@pytest.mark.parametrize("block", [2 << 20, 1 << 20, 65536, 4096, 1000, 700])
+def test_loader_blocks_match_oracle(block, syn_data):
+    for path in (os.path.join(GOLDEN, "data", "small_train-00000"), syn_data[0] + "-00000"):
+        if block < 4096 and "syn" in path:
+            continue
+        a = list(api.Loader(path, block))
+        b = list(O.load_blocks(path, block))
+        assert len(a) == len(b) and len(a) > 0
+        for (rp, k, l), (rp2, k2, l2) in zip(a, b):
+            assert np.array_equal(rp.astype(np.int64), rp2)
+            assert np.array_equal(k, k2)
+            assert np.array_equal(l.astype(np.int32), l2)
+
+
+def test_loader_edge_cases(tmp_path):
+    # CRLF line ends, float labels, trailing space, missing final newline, empty file
+    p = tmp_path / "edge-00000"
+    p.write_bytes(b"1\t0:12:0.5 1:34:0.5\r\n0.0\t2:56:1 \n1e-9\t3:7:1\n0.5\t4:8:1 5:9:1")
+    a = list(api.Loader(str(p), 1 << 20))
+    b = list(O.load_blocks(str(p), 1 << 20))
+    assert len(a) == 1 and len(b) == 1
+    rp, k, l = a[0]
+    assert list(l) == [1, 0, 0, 1]
+    assert list(rp) == [0, 2, 3, 4, 6]
+    assert np.array_equal(k, b[0][1]) and np.array_equal(rp.astype(np.int64), b[0][0])
+    assert int(k[0]) == O.std_hash(b"12") and int(k[5]) == O.std_hash(b"9")
+    e = tmp_path / "empty-00000"
+    e.write_bytes(b"")
+    assert list(api.Loader(str(e), 1 << 20)) == []
+    with pytest.raises(api.XflowError):
+        api.Loader(str(tmp_path / "missing-00000"), 1 << 20)
+
+
+def test_auc_logloss_matches_oracle():
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 200, 5000):
+        lab = (rng.random(n) < 0.3).astype(np.int32)
+        p = rng.random(n).astype(np.float32) * 0.98 + 0.01
+        p[: n // 4] = p[0]  # ties
+        a, b = api.auc_logloss(lab, p), O.auc_logloss(lab, p)
+        assert a["tp"] == b["tp"] and a["fp"] == b["fp"]
+        assert a["logloss"] == b["logloss"]
+        assert (np.isnan(a["auc"]) and np.isnan(b["auc"])) or a["auc"] == b["auc"]

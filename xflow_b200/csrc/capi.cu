@@ -1,0 +1,708 @@
+// C ABI layers 2 (parameter table) and 3 (fused worker step) of include/xflow_b200.h.
+// Host orchestration only — every byte of table state lives in HBM and is touched only by the
+// kernels in kernels.cu.  There is no CPU fallback anywhere in this file.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "internal.h"
+
+// -------------------------------------------------------------------------------------------------
+// errors
+// -------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void xf_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+XF_DLL const char* xf_last_error(void) { return g_err; }
+XF_DLL int xf_version(void) { return 100; }
+XF_DLL int xf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int XfDevBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return XF_OK;
+  size_t want = std::max(bytes, cap + cap / 2);
+  if (p) XF_CUDA_TRY(cudaFree(p));
+  p = nullptr;
+  cap = 0;
+  XF_CUDA_TRY(cudaMalloc(&p, want));
+  cap = want;
+  return XF_OK;
+}
+void XfDevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+int XfPinBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return XF_OK;
+  size_t want = std::max(bytes, cap + cap / 2);
+  if (p) XF_CUDA_TRY(cudaFreeHost(p));
+  p = nullptr;
+  cap = 0;
+  XF_CUDA_TRY(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+  cap = want;
+  return XF_OK;
+}
+void XfPinBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// table
+// -------------------------------------------------------------------------------------------------
+XF_DLL int xf_table_config_default(xf_table_config* cfg) {
+  if (!cfg) return XF_ERR_ARG;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->device = 0;
+  cfg->latent_dim = 0;
+  cfg->optimizer = XF_OPTIMIZER_FTRL;  // server.h:24,28
+  cfg->alpha = 5e-2f;                  // ftrl.h:17
+  cfg->beta = 1.0f;                    // ftrl.h:18
+  cfg->lambda1 = 5e-5f;                // ftrl.h:19
+  cfg->lambda2 = 10.0f;                // ftrl.h:20
+  cfg->learning_rate = 0.001f;         // sgd.h:16
+  cfg->v_init = XF_VINIT_DEFAULT;
+  cfg->seed = 0;
+  cfg->capacity = 0;
+  cfg->shard_index = 0;
+  cfg->num_shards = 1;
+  return XF_OK;
+}
+
+static uint64_t xf_pow2_at_least(uint64_t x) {
+  uint64_t p = 1024;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+int xf_table::alloc_table(uint64_t capacity) {
+  capacity = xf_pow2_at_least(capacity);
+  if (capacity > (1ull << 31)) {
+    xf_set_error("table capacity %llu exceeds 2^31 slots", (unsigned long long)capacity);
+    return XF_ERR_FULL;
+  }
+  const uint32_t stride = xf_row_stride(cfg.latent_dim, cfg.optimizer);
+  uint8_t* base = nullptr;
+  XF_CUDA_TRY(cudaMalloc(&base, capacity * (uint64_t)stride));
+  view.base = base;
+  view.mask = capacity - 1;
+  uint32_t lg = 0;
+  while ((1ull << lg) < capacity) ++lg;
+  view.log2cap = lg;
+  view.stride = stride;
+  xf_launch_fill(view, stream);
+  ++launches;
+  XF_CUDA_TRY(cudaGetLastError());
+  return XF_OK;
+}
+
+int xf_table::check_error() {
+  int e = 0;
+  XF_CUDA_TRY(cudaMemcpyAsync(&e, d_error, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  XF_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (e) {
+    xf_set_error("table probe sequence overflowed (table full)");
+    return XF_ERR_FULL;
+  }
+  return XF_OK;
+}
+
+int xf_table::grow(uint64_t new_capacity) {
+  XfTableView old = view;
+  XF_CUDA_TRY(cudaMemsetAsync(d_size, 0, sizeof(unsigned long long), stream));
+  XF_TRY(alloc_table(new_capacity));
+  xf_launch_rehash(old, view, stream);
+  ++launches;
+  XF_CUDA_TRY(cudaStreamSynchronize(stream));
+  XF_CUDA_TRY(cudaFree(old.base));
+  return XF_OK;
+}
+
+int xf_table::ensure_room(uint64_t incoming) {
+  const uint64_t cap = view.mask + 1;
+  size_bound += incoming;
+  if (size_bound * 2 <= cap) return XF_OK;
+  unsigned long long actual = 0;
+  XF_CUDA_TRY(cudaMemcpyAsync(&actual, d_size, sizeof(actual), cudaMemcpyDeviceToHost, stream));
+  XF_CUDA_TRY(cudaStreamSynchronize(stream));
+  size_bound = actual + incoming;
+  uint64_t want = cap;
+  while (size_bound * 2 > want) want <<= 1;
+  if (want != cap) XF_TRY(grow(want));
+  return XF_OK;
+}
+
+XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
+  if (!out || !cfg) { xf_set_error("null argument"); return XF_ERR_ARG; }
+  if (cfg->latent_dim < 0 || cfg->latent_dim > 1024 || cfg->num_shards < 1 || cfg->shard_index < 0 ||
+      cfg->shard_index >= cfg->num_shards || (cfg->optimizer != XF_OPTIMIZER_FTRL && cfg->optimizer != XF_OPTIMIZER_SGD)) {
+    xf_set_error("bad table config");
+    return XF_ERR_ARG;
+  }
+  XF_CUDA_TRY(cudaSetDevice(cfg->device));
+  xf_table* t = new xf_table;
+  t->cfg = *cfg;
+  memset(&t->view, 0, sizeof(t->view));
+  XF_CUDA_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+  XF_CUDA_TRY(cudaMalloc(&t->d_size, sizeof(unsigned long long)));
+  XF_CUDA_TRY(cudaMalloc(&t->d_error, sizeof(int)));
+  XF_CUDA_TRY(cudaMemsetAsync(t->d_size, 0, sizeof(unsigned long long), t->stream));
+  XF_CUDA_TRY(cudaMemsetAsync(t->d_error, 0, sizeof(int), t->stream));
+  XfTableView& v = t->view;
+  v.K = cfg->latent_dim;
+  v.opt = cfg->optimizer == XF_OPTIMIZER_FTRL ? XF_OPT_FTRL : XF_OPT_SGD;
+  v.alpha = cfg->alpha; v.beta = cfg->beta; v.lambda1 = cfg->lambda1; v.lambda2 = cfg->lambda2;
+  v.learning_rate = cfg->learning_rate;
+  v.seed = cfg->seed;
+  v.v_const = 0.001f;  // sgd.h:68-70
+  if (cfg->v_init == XF_VINIT_ZERO) v.v_init = XF_INIT_ZERO;
+  else if (cfg->v_init == XF_VINIT_COUNTER) v.v_init = XF_INIT_COUNTER;
+  else v.v_init = (v.opt == XF_OPT_FTRL) ? XF_INIT_COUNTER : XF_INIT_DEFAULT;
+  v.size = t->d_size;
+  v.error = t->d_error;
+  int r = t->alloc_table(cfg->capacity ? cfg->capacity : (1ull << 20));
+  if (r != XF_OK) { delete t; return r; }
+  XF_CUDA_TRY(cudaStreamSynchronize(t->stream));
+  *out = t;
+  return XF_OK;
+}
+
+XF_DLL int xf_table_destroy(xf_table* t) {
+  if (!t) return XF_OK;
+  cudaSetDevice(t->cfg.device);
+  cudaStreamSynchronize(t->stream);
+  if (t->view.base) cudaFree(t->view.base);
+  cudaFree(t->d_size);
+  cudaFree(t->d_error);
+  t->s_keys.release(); t->s_slots.release(); t->s_w.release(); t->s_v.release();
+  t->s_nw.release(); t->s_zw.release(); t->s_nv.release(); t->s_zv.release(); t->s_present.release();
+  if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
+  delete t;
+  return XF_OK;
+}
+
+XF_DLL int xf_table_set_stream(xf_table* t, void* cuda_stream) {
+  if (!t) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaStreamSynchronize(t->stream));
+  if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
+  if (cuda_stream) {
+    t->stream = (cudaStream_t)cuda_stream;
+    t->own_stream = false;
+  } else {
+    XF_CUDA_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    t->own_stream = true;
+  }
+  return XF_OK;
+}
+
+XF_DLL int xf_table_sync(xf_table* t) {
+  if (!t) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaStreamSynchronize(t->stream));
+  return t->check_error();
+}
+
+XF_DLL int xf_table_size(xf_table* t, uint64_t* n_keys) {
+  if (!t || !n_keys) return XF_ERR_ARG;
+  unsigned long long v = 0;
+  XF_CUDA_TRY(cudaMemcpyAsync(&v, t->d_size, sizeof(v), cudaMemcpyDeviceToHost, t->stream));
+  XF_CUDA_TRY(cudaStreamSynchronize(t->stream));
+  *n_keys = v;
+  return XF_OK;
+}
+XF_DLL int xf_table_capacity(xf_table* t, uint64_t* n_slots) {
+  if (!t || !n_slots) return XF_ERR_ARG;
+  *n_slots = t->view.mask + 1;
+  return XF_OK;
+}
+XF_DLL int xf_table_row_bytes(xf_table* t, uint32_t* bytes) {
+  if (!t || !bytes) return XF_ERR_ARG;
+  *bytes = t->view.stride;
+  return XF_OK;
+}
+XF_DLL int xf_table_reserve(xf_table* t, uint64_t n_keys) {
+  if (!t) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
+  uint64_t want = xf_pow2_at_least(n_keys * 2);
+  if (want > t->view.mask + 1) XF_TRY(t->grow(want));
+  return XF_OK;
+}
+
+XF_DLL int xf_table_pull_device(xf_table* t, const uint64_t* d_keys, uint64_t n, float* d_w_out, float* d_v_out) {
+  if (!t || (!d_keys && n)) return XF_ERR_ARG;
+  if (n == 0) return XF_OK;
+  XF_TRY(t->ensure_room(n));
+  XF_TRY(t->s_slots.ensure(n * sizeof(uint32_t)));
+  xf_launch_probe(t->view, d_keys, n, true, t->s_slots.as<uint32_t>(), d_w_out, t->stream);
+  ++t->launches;
+  if (d_v_out && t->view.K > 0) {
+    xf_launch_gather_v(t->view, t->s_slots.as<uint32_t>(), d_keys, n, d_v_out, t->stream);
+    ++t->launches;
+  }
+  XF_CUDA_TRY(cudaGetLastError());
+  return XF_OK;
+}
+
+XF_DLL int xf_table_push_device(xf_table* t, const uint64_t* d_keys, uint64_t n, const float* d_gw, const float* d_gv) {
+  if (!t || (!d_keys && n)) return XF_ERR_ARG;
+  if (n == 0) return XF_OK;
+  if (d_gv && t->view.K == 0) d_gv = nullptr;
+  XF_TRY(t->ensure_room(n));
+  XF_TRY(t->s_slots.ensure(n * sizeof(uint32_t)));
+  xf_launch_probe(t->view, d_keys, n, true, t->s_slots.as<uint32_t>(), nullptr, t->stream);
+  xf_launch_update_pushed(t->view, t->s_slots.as<uint32_t>(), n, d_gw, d_gv, t->stream);
+  t->launches += 2;
+  XF_CUDA_TRY(cudaGetLastError());
+  return XF_OK;
+}
+
+XF_DLL int xf_table_pull(xf_table* t, const uint64_t* keys, uint64_t n, float* w_out, float* v_out) {
+  if (!t || (!keys && n)) return XF_ERR_ARG;
+  if (n == 0) return XF_OK;
+  XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
+  const int K = t->view.K;
+  XF_TRY(t->s_keys.ensure(n * 8));
+  XF_TRY(t->s_w.ensure(n * 4));
+  if (v_out && K) XF_TRY(t->s_v.ensure(n * 4 * (size_t)K));
+  XF_CUDA_TRY(cudaMemcpyAsync(t->s_keys.p, keys, n * 8, cudaMemcpyHostToDevice, t->stream));
+  XF_TRY(xf_table_pull_device(t, t->s_keys.as<uint64_t>(), n, t->s_w.as<float>(), (v_out && K) ? t->s_v.as<float>() : nullptr));
+  if (w_out) XF_CUDA_TRY(cudaMemcpyAsync(w_out, t->s_w.p, n * 4, cudaMemcpyDeviceToHost, t->stream));
+  if (v_out && K) XF_CUDA_TRY(cudaMemcpyAsync(v_out, t->s_v.p, n * 4 * (size_t)K, cudaMemcpyDeviceToHost, t->stream));
+  return xf_table_sync(t);
+}
+
+XF_DLL int xf_table_push(xf_table* t, const uint64_t* keys, uint64_t n, const float* gw, const float* gv) {
+  if (!t || (!keys && n)) return XF_ERR_ARG;
+  if (n == 0) return XF_OK;
+  XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
+  const int K = t->view.K;
+  XF_TRY(t->s_keys.ensure(n * 8));
+  XF_CUDA_TRY(cudaMemcpyAsync(t->s_keys.p, keys, n * 8, cudaMemcpyHostToDevice, t->stream));
+  if (gw) {
+    XF_TRY(t->s_w.ensure(n * 4));
+    XF_CUDA_TRY(cudaMemcpyAsync(t->s_w.p, gw, n * 4, cudaMemcpyHostToDevice, t->stream));
+  }
+  if (gv && K) {
+    XF_TRY(t->s_v.ensure(n * 4 * (size_t)K));
+    XF_CUDA_TRY(cudaMemcpyAsync(t->s_v.p, gv, n * 4 * (size_t)K, cudaMemcpyHostToDevice, t->stream));
+  }
+  XF_TRY(xf_table_push_device(t, t->s_keys.as<uint64_t>(), n, gw ? t->s_w.as<float>() : nullptr,
+                              (gv && K) ? t->s_v.as<float>() : nullptr));
+  return xf_table_sync(t);
+}
+
+static int xf_h2d_opt(XfDevBuf& b, const float* src, size_t count, cudaStream_t st, float** dptr) {
+  *dptr = nullptr;
+  if (!src || count == 0) return XF_OK;
+  XF_TRY(b.ensure(count * 4));
+  XF_CUDA_TRY(cudaMemcpyAsync(b.p, src, count * 4, cudaMemcpyHostToDevice, st));
+  *dptr = b.as<float>();
+  return XF_OK;
+}
+
+XF_DLL int xf_table_import(xf_table* t, const uint64_t* keys, uint64_t n, const float* w, const float* nw,
+                           const float* zw, const float* v, const float* nv, const float* zv) {
+  if (!t || (!keys && n)) return XF_ERR_ARG;
+  if (n == 0) return XF_OK;
+  XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
+  const size_t K = (size_t)t->view.K;
+  XF_TRY(t->ensure_room(n));
+  XF_TRY(t->s_keys.ensure(n * 8));
+  XF_TRY(t->s_slots.ensure(n * 4));
+  XF_CUDA_TRY(cudaMemcpyAsync(t->s_keys.p, keys, n * 8, cudaMemcpyHostToDevice, t->stream));
+  float *dw, *dnw, *dzw, *dv, *dnv, *dzv;
+  XF_TRY(xf_h2d_opt(t->s_w, w, n, t->stream, &dw));
+  XF_TRY(xf_h2d_opt(t->s_nw, nw, n, t->stream, &dnw));
+  XF_TRY(xf_h2d_opt(t->s_zw, zw, n, t->stream, &dzw));
+  XF_TRY(xf_h2d_opt(t->s_v, K ? v : nullptr, n * K, t->stream, &dv));
+  XF_TRY(xf_h2d_opt(t->s_nv, K ? nv : nullptr, n * K, t->stream, &dnv));
+  XF_TRY(xf_h2d_opt(t->s_zv, K ? zv : nullptr, n * K, t->stream, &dzv));
+  xf_launch_probe(t->view, t->s_keys.as<uint64_t>(), n, true, t->s_slots.as<uint32_t>(), nullptr, t->stream);
+  xf_launch_import(t->view, t->s_slots.as<uint32_t>(), n, dw, dnw, dzw, dv, dnv, dzv, t->stream);
+  t->launches += 2;
+  XF_CUDA_TRY(cudaGetLastError());
+  return xf_table_sync(t);
+}
+
+XF_DLL int xf_table_export(xf_table* t, const uint64_t* keys, uint64_t n, float* w, float* nw, float* zw,
+                           float* v, float* nv, float* zv, uint8_t* present) {
+  if (!t || (!keys && n)) return XF_ERR_ARG;
+  if (n == 0) return XF_OK;
+  XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
+  const size_t K = (size_t)t->view.K;
+  XF_TRY(t->s_keys.ensure(n * 8));
+  XF_TRY(t->s_slots.ensure(n * 4));
+  XF_TRY(t->s_w.ensure(n * 4));
+  XF_TRY(t->s_nw.ensure(n * 4));
+  XF_TRY(t->s_zw.ensure(n * 4));
+  XF_TRY(t->s_present.ensure(n));
+  if (K) {
+    XF_TRY(t->s_v.ensure(n * K * 4));
+    XF_TRY(t->s_nv.ensure(n * K * 4));
+    XF_TRY(t->s_zv.ensure(n * K * 4));
+  }
+  XF_CUDA_TRY(cudaMemcpyAsync(t->s_keys.p, keys, n * 8, cudaMemcpyHostToDevice, t->stream));
+  xf_launch_probe(t->view, t->s_keys.as<uint64_t>(), n, false, t->s_slots.as<uint32_t>(), nullptr, t->stream);
+  xf_launch_export(t->view, t->s_slots.as<uint32_t>(), t->s_keys.as<uint64_t>(), n, t->s_w.as<float>(),
+                   t->s_nw.as<float>(), t->s_zw.as<float>(), K ? t->s_v.as<float>() : nullptr,
+                   K ? t->s_nv.as<float>() : nullptr, K ? t->s_zv.as<float>() : nullptr,
+                   t->s_present.as<uint8_t>(), t->stream);
+  t->launches += 2;
+  XF_CUDA_TRY(cudaGetLastError());
+  if (w) XF_CUDA_TRY(cudaMemcpyAsync(w, t->s_w.p, n * 4, cudaMemcpyDeviceToHost, t->stream));
+  if (nw) XF_CUDA_TRY(cudaMemcpyAsync(nw, t->s_nw.p, n * 4, cudaMemcpyDeviceToHost, t->stream));
+  if (zw) XF_CUDA_TRY(cudaMemcpyAsync(zw, t->s_zw.p, n * 4, cudaMemcpyDeviceToHost, t->stream));
+  if (present) XF_CUDA_TRY(cudaMemcpyAsync(present, t->s_present.p, n, cudaMemcpyDeviceToHost, t->stream));
+  if (K && v) XF_CUDA_TRY(cudaMemcpyAsync(v, t->s_v.p, n * K * 4, cudaMemcpyDeviceToHost, t->stream));
+  if (K && nv) XF_CUDA_TRY(cudaMemcpyAsync(nv, t->s_nv.p, n * K * 4, cudaMemcpyDeviceToHost, t->stream));
+  if (K && zv) XF_CUDA_TRY(cudaMemcpyAsync(zv, t->s_zv.p, n * K * 4, cudaMemcpyDeviceToHost, t->stream));
+  return xf_table_sync(t);
+}
+
+XF_DLL int xf_table_list_keys(xf_table* t, uint64_t* keys_out, uint64_t max_keys, uint64_t* n_out) {
+  if (!t || !n_out) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
+  XF_TRY(t->s_keys.ensure(std::max<uint64_t>(max_keys, 1) * 8));
+  unsigned long long* d_count = nullptr;
+  XF_CUDA_TRY(cudaMalloc(&d_count, 8));
+  XF_CUDA_TRY(cudaMemsetAsync(d_count, 0, 8, t->stream));
+  xf_launch_list_keys(t->view, t->s_keys.as<uint64_t>(), d_count, max_keys, t->stream);
+  ++t->launches;
+  unsigned long long cnt = 0;
+  XF_CUDA_TRY(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, t->stream));
+  XF_CUDA_TRY(cudaStreamSynchronize(t->stream));
+  cudaFree(d_count);
+  uint64_t ncopy = std::min<uint64_t>(cnt, max_keys);
+  if (keys_out && ncopy) XF_CUDA_TRY(cudaMemcpy(keys_out, t->s_keys.p, ncopy * 8, cudaMemcpyDeviceToHost));
+  *n_out = cnt;
+  return XF_OK;
+}
+
+// checkpoint file: "XFTB" u64 n, u32 K, u32 has_nz, keys[n], w[n], (nw,zw), v[n*K], (nv,zv), present[n]
+XF_DLL int xf_table_save(xf_table* t, const char* path) {
+  if (!t || !path) return XF_ERR_ARG;
+  uint64_t n = 0;
+  XF_TRY(xf_table_size(t, &n));
+  std::vector<uint64_t> keys(n ? n : 1);
+  uint64_t got = 0;
+  XF_TRY(xf_table_list_keys(t, keys.data(), n, &got));
+  n = std::min(n, got);
+  std::sort(keys.begin(), keys.begin() + n);
+  const size_t K = (size_t)t->view.K;
+  const uint32_t has_nz = t->view.opt == XF_OPT_FTRL ? 1 : 0;
+  std::vector<float> w(n), nw(n), zw(n), v(n * K), nv(n * K), zv(n * K);
+  std::vector<uint8_t> present(n);
+  XF_TRY(xf_table_export(t, keys.data(), n, w.data(), nw.data(), zw.data(), K ? v.data() : nullptr,
+                         K ? nv.data() : nullptr, K ? zv.data() : nullptr, present.data()));
+  FILE* f = fopen(path, "wb");
+  if (!f) { xf_set_error("cannot open %s for writing", path); return XF_ERR_IO; }
+  uint32_t K32 = (uint32_t)K;
+  fwrite("XFTB", 1, 4, f);
+  fwrite(&n, 8, 1, f); fwrite(&K32, 4, 1, f); fwrite(&has_nz, 4, 1, f);
+  fwrite(keys.data(), 8, n, f);
+  fwrite(w.data(), 4, n, f);
+  if (has_nz) { fwrite(nw.data(), 4, n, f); fwrite(zw.data(), 4, n, f); }
+  fwrite(v.data(), 4, n * K, f);
+  if (has_nz) { fwrite(nv.data(), 4, n * K, f); fwrite(zv.data(), 4, n * K, f); }
+  fwrite(present.data(), 1, n, f);
+  fclose(f);
+  return XF_OK;
+}
+
+XF_DLL int xf_table_load(xf_table* t, const char* path) {
+  if (!t || !path) return XF_ERR_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) { xf_set_error("cannot open %s", path); return XF_ERR_IO; }
+  char magic[4];
+  uint64_t n = 0;
+  uint32_t K32 = 0, has_nz = 0;
+  bool ok = fread(magic, 1, 4, f) == 4 && memcmp(magic, "XFTB", 4) == 0 && fread(&n, 8, 1, f) == 1 &&
+            fread(&K32, 4, 1, f) == 1 && fread(&has_nz, 4, 1, f) == 1;
+  if (!ok || (int)K32 != t->view.K) {
+    fclose(f);
+    xf_set_error("bad checkpoint %s (K=%u, table K=%d)", path, K32, t->view.K);
+    return XF_ERR_IO;
+  }
+  const size_t K = K32;
+  std::vector<uint64_t> keys(n);
+  std::vector<float> w(n), nw(n), zw(n), v(n * K), nv(n * K), zv(n * K);
+  ok = fread(keys.data(), 8, n, f) == n && fread(w.data(), 4, n, f) == n;
+  if (ok && has_nz) ok = fread(nw.data(), 4, n, f) == n && fread(zw.data(), 4, n, f) == n;
+  if (ok && K) ok = fread(v.data(), 4, n * K, f) == n * K;
+  if (ok && K && has_nz) ok = fread(nv.data(), 4, n * K, f) == n * K && fread(zv.data(), 4, n * K, f) == n * K;
+  fclose(f);
+  if (!ok) { xf_set_error("truncated checkpoint %s", path); return XF_ERR_IO; }
+  return xf_table_import(t, keys.data(), n, w.data(), has_nz ? nw.data() : nullptr, has_nz ? zw.data() : nullptr,
+                         K ? v.data() : nullptr, (K && has_nz) ? nv.data() : nullptr,
+                         (K && has_nz) ? zv.data() : nullptr);
+}
+
+XF_DLL int xf_shard_of(uint64_t key, int num_shards) {
+  if (num_shards <= 1) return 0;
+  const uint64_t width = 0xFFFFFFFFFFFFFFFFull / (uint64_t)num_shards;  // postoffice.cc:138-140
+  const uint64_t s = key / width;
+  return (int)(s < (uint64_t)num_shards ? s : (uint64_t)num_shards - 1);
+}
+
+// -------------------------------------------------------------------------------------------------
+// trainer
+// -------------------------------------------------------------------------------------------------
+XF_DLL int xf_trainer_create(xf_trainer** out, xf_table* table, xf_comm* comm, const xf_trainer_config* cfg) {
+  if (!out || !table || !cfg) { xf_set_error("null argument"); return XF_ERR_ARG; }
+  if (cfg->model == XF_MODEL_FM && table->view.K <= 0) { xf_set_error("FM needs latent_dim > 0"); return XF_ERR_ARG; }
+  if (cfg->model == XF_MODEL_LR && table->view.K != 0) { xf_set_error("LR needs latent_dim == 0"); return XF_ERR_ARG; }
+  if (cfg->max_rows == 0 || cfg->max_nnz == 0) { xf_set_error("max_rows/max_nnz must be > 0"); return XF_ERR_ARG; }
+  XF_CUDA_TRY(cudaSetDevice(table->cfg.device));
+  xf_trainer* tr = new xf_trainer;
+  tr->table = table;
+  tr->comm = comm;
+  tr->cfg = *cfg;
+  XF_CUDA_TRY(cudaStreamCreateWithFlags(&tr->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->buf[i].copied, cudaEventDisableTiming));
+    XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->buf[i].consumed, cudaEventDisableTiming));
+    XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->buf[i].staged, cudaEventDisableTiming));
+  }
+  XF_TRY(tr->touched.ensure((size_t)cfg->max_nnz * 4));
+  XF_TRY(tr->loss.ensure((size_t)cfg->max_rows * 4));
+  XF_TRY(tr->pctr.ensure((size_t)cfg->max_rows * 4));
+  XF_CUDA_TRY(cudaMalloc(&tr->d_touched_cnt, sizeof(unsigned int)));
+  XF_CUDA_TRY(cudaMalloc(&tr->d_unique_total, sizeof(unsigned long long)));
+  XF_CUDA_TRY(cudaMalloc(&tr->d_abs_loss, 2 * sizeof(float)));
+  XF_CUDA_TRY(cudaHostAlloc(&tr->h_abs_loss, 2 * sizeof(float), cudaHostAllocDefault));
+  XF_CUDA_TRY(cudaMemsetAsync(tr->d_touched_cnt, 0, sizeof(unsigned int), table->stream));
+  XF_CUDA_TRY(cudaMemsetAsync(tr->d_unique_total, 0, sizeof(unsigned long long), table->stream));
+  XF_CUDA_TRY(cudaMemsetAsync(tr->d_abs_loss, 0, 2 * sizeof(float), table->stream));
+  XF_CUDA_TRY(cudaStreamSynchronize(table->stream));
+  if (comm && xf_comm_nranks(comm) > 1) {
+    if (table->cfg.num_shards != xf_comm_nranks(comm) || table->cfg.shard_index != xf_comm_rank(comm)) {
+      xf_set_error("table shard (%d of %d) does not match comm rank (%d of %d)", table->cfg.shard_index,
+                   table->cfg.num_shards, xf_comm_rank(comm), xf_comm_nranks(comm));
+      delete tr;
+      return XF_ERR_ARG;
+    }
+    int r = xf_mg_create(tr);
+    if (r != XF_OK) { delete tr; return r; }
+  }
+  *out = tr;
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
+  if (!tr) return XF_OK;
+  cudaSetDevice(tr->table->cfg.device);
+  cudaStreamSynchronize(tr->table->stream);
+  cudaStreamSynchronize(tr->copy_stream);
+  if (tr->mg) xf_mg_destroy(tr);
+  for (int i = 0; i < 2; ++i) {
+    XfBatchBuf& b = tr->buf[i];
+    b.row_ptr.release(); b.keys.release(); b.labels.release();
+    b.h_row_ptr.release(); b.h_keys.release(); b.h_labels.release();
+    cudaEventDestroy(b.copied); cudaEventDestroy(b.consumed); cudaEventDestroy(b.staged);
+  }
+  tr->touched.release(); tr->loss.release(); tr->pctr.release();
+  cudaFree(tr->d_touched_cnt); cudaFree(tr->d_unique_total); cudaFree(tr->d_abs_loss);
+  cudaFreeHost(tr->h_abs_loss);
+  cudaStreamDestroy(tr->copy_stream);
+  delete tr;
+  return XF_OK;
+}
+
+static int xf_check_batch(xf_trainer* tr, uint32_t rows, uint32_t nnz) {
+  if (rows > tr->cfg.max_rows || nnz > tr->cfg.max_nnz) {
+    xf_set_error("batch (%u rows, %u tokens) exceeds trainer limits (%u, %u)", rows, nnz, tr->cfg.max_rows,
+                 tr->cfg.max_nnz);
+    return XF_ERR_ARG;
+  }
+  return XF_OK;
+}
+
+// the step proper, on device-resident CSR; mode 0 = train, 1 = predict
+static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys,
+                               const uint8_t* d_labels, uint32_t rows, uint32_t nnz, int mode, float* d_abs) {
+  xf_table* t = tr->table;
+  if (rows == 0) return XF_OK;
+  if (tr->mg) return xf_mg_step(tr, d_row_ptr, d_keys, d_labels, rows, nnz, mode, d_abs);
+  XF_TRY(t->ensure_room(nnz));
+  cudaStream_t st = t->stream;
+  xf_launch_step(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
+                 tr->d_touched_cnt, (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
+                 mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
+  ++tr->launches;
+  if (mode == 0) {
+    // Push + server-side optimizer: one FTRL/SGD step per touched key with g / rows
+    xf_launch_update_touched(t->view, tr->touched.as<uint32_t>(), tr->d_touched_cnt, nnz, (double)rows, st);
+    xf_launch_batch_end(tr->d_touched_cnt, tr->d_unique_total, st);
+    tr->launches += 2;
+  }
+  XF_CUDA_TRY(cudaGetLastError());
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_step_device(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys,
+                                  const uint8_t* d_labels, uint32_t rows, uint32_t nnz) {
+  if (!tr || !d_row_ptr || !d_keys || !d_labels) return XF_ERR_ARG;
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  XF_TRY(xf_step_device_impl(tr, d_row_ptr, d_keys, d_labels, rows, nnz, 0, nullptr));
+  ++tr->n_steps;
+  tr->n_rows += rows;
+  tr->n_nnz += nnz;
+  tr->last_rows = rows;
+  return XF_OK;
+}
+
+static bool xf_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// stage one host array into buffer set `b` (pinned source: DMA directly; pageable: copy through the
+// set's pinned staging) and enqueue the H2D on the copy stream
+static int xf_stage(xf_trainer* tr, XfDevBuf& dev, XfPinBuf& pin, const void* src, size_t bytes, bool staging_free) {
+  if (bytes == 0) return XF_OK;
+  XF_TRY(dev.ensure(bytes));
+  const void* from = src;
+  if (!xf_is_pinned(src)) {
+    (void)staging_free;
+    XF_TRY(pin.ensure(bytes));
+    memcpy(pin.p, src, bytes);
+    from = pin.p;
+  }
+  XF_CUDA_TRY(cudaMemcpyAsync(dev.p, from, bytes, cudaMemcpyHostToDevice, tr->copy_stream));
+  return XF_OK;
+}
+
+static int xf_upload_batch(xf_trainer* tr, XfBatchBuf& b, const uint32_t* row_ptr, const uint64_t* keys,
+                           const uint8_t* labels, uint32_t rows, uint32_t nnz) {
+  // the device buffers of this set may still be read by the step issued two calls ago
+  XF_CUDA_TRY(cudaStreamWaitEvent(tr->copy_stream, b.consumed, 0));
+  // its pinned staging may still be the source of that step's H2D
+  XF_CUDA_TRY(cudaEventSynchronize(b.staged));
+  XF_TRY(xf_stage(tr, b.row_ptr, b.h_row_ptr, row_ptr, ((size_t)rows + 1) * 4, true));
+  XF_TRY(xf_stage(tr, b.keys, b.h_keys, keys, (size_t)nnz * 8, true));
+  if (labels) XF_TRY(xf_stage(tr, b.labels, b.h_labels, labels, (size_t)rows, true));
+  XF_CUDA_TRY(cudaEventRecord(b.staged, tr->copy_stream));
+  XF_CUDA_TRY(cudaEventRecord(b.copied, tr->copy_stream));
+  XF_CUDA_TRY(cudaStreamWaitEvent(tr->table->stream, b.copied, 0));
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_step_host(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys,
+                                const uint8_t* labels, uint32_t rows, uint32_t nnz, float* mean_abs_loss) {
+  if (!tr || !row_ptr || (!keys && nnz) || !labels) return XF_ERR_ARG;
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  if (rows == 0) { if (mean_abs_loss) *mean_abs_loss = 0.f; return XF_OK; }
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const int slot = (int)(tr->step_index & 1);
+  XfBatchBuf& b = tr->buf[slot];
+  ++tr->step_index;
+  XF_TRY(xf_upload_batch(tr, b, row_ptr, keys, labels, rows, nnz));
+  cudaStream_t st = tr->table->stream;
+  XF_CUDA_TRY(cudaMemsetAsync(tr->d_abs_loss + slot, 0, sizeof(float), st));
+  XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows,
+                             nnz, 0, tr->d_abs_loss + slot));
+  XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
+  ++tr->n_steps;
+  tr->n_rows += rows;
+  tr->n_nnz += nnz;
+  tr->last_rows = rows;
+  if (mean_abs_loss) {
+    XF_CUDA_TRY(cudaMemcpyAsync(tr->h_abs_loss + slot, tr->d_abs_loss + slot, sizeof(float),
+                                cudaMemcpyDeviceToHost, st));
+    XF_CUDA_TRY(cudaStreamSynchronize(st));
+    *mean_abs_loss = tr->h_abs_loss[slot] / (float)rows;
+  }
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_predict_host(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys, uint32_t rows,
+                                   uint32_t nnz, float* pctr_out) {
+  if (!tr || !row_ptr || (!keys && nnz) || !pctr_out) return XF_ERR_ARG;
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  if (rows == 0) return XF_OK;
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const int slot = (int)(tr->step_index & 1);
+  XfBatchBuf& b = tr->buf[slot];
+  ++tr->step_index;
+  XF_TRY(xf_upload_batch(tr, b, row_ptr, keys, nullptr, rows, nnz));
+  cudaStream_t st = tr->table->stream;
+  XF_TRY(b.labels.ensure(rows));  // unused by mode 1 but must be a valid pointer
+  XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows,
+                             nnz, 1, nullptr));
+  XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
+  XF_CUDA_TRY(cudaMemcpyAsync(pctr_out, tr->pctr.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  return tr->table->check_error();
+}
+
+XF_DLL int xf_trainer_init_push(xf_trainer* tr) {
+  if (!tr) return XF_ERR_ARG;
+  xf_table* t = tr->table;
+  // Every worker pushes key 0 with a zero gradient once (lr_worker.cc:180-182, fm_worker.cc:248-252).
+  // Key 0 belongs to shard 0; other shards have nothing to do.
+  if (xf_shard_of(0, t->cfg.num_shards) != t->cfg.shard_index) return XF_OK;
+  uint64_t key = 0;
+  float gw = 0.f;
+  std::vector<float> gv((size_t)std::max(t->view.K, 1), 0.f);
+  int reps = tr->comm ? xf_comm_nranks(tr->comm) : 1;  // one init push per worker rank
+  for (int r = 0; r < reps; ++r) XF_TRY(xf_table_push(t, &key, 1, &gw, t->view.K ? gv.data() : nullptr));
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_get_loss(xf_trainer* tr, float* loss_out, uint32_t rows) {
+  if (!tr || !loss_out) return XF_ERR_ARG;
+  if (!tr->cfg.keep_loss) { xf_set_error("trainer created with keep_loss = 0"); return XF_ERR_STATE; }
+  if (rows > tr->cfg.max_rows) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaMemcpyAsync(loss_out, tr->loss.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, tr->table->stream));
+  XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_stats(xf_trainer* tr, uint64_t* steps, uint64_t* rows, uint64_t* nnz, uint64_t* unique_keys) {
+  if (!tr) return XF_ERR_ARG;
+  if (steps) *steps = tr->n_steps;
+  if (rows) *rows = tr->n_rows;
+  if (nnz) *nnz = tr->n_nnz;
+  if (unique_keys) {
+    unsigned long long u = 0;
+    XF_CUDA_TRY(cudaMemcpyAsync(&u, tr->d_unique_total, sizeof(u), cudaMemcpyDeviceToHost, tr->table->stream));
+    XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
+    *unique_keys = u;
+  }
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_launches(xf_trainer* tr, uint64_t* launches) {
+  if (!tr || !launches) return XF_ERR_ARG;
+  *launches = tr->launches + tr->table->launches;
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_sync(xf_trainer* tr) {
+  if (!tr) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaStreamSynchronize(tr->copy_stream));
+  return xf_table_sync(tr->table);
+}
+
+XF_DLL int xf_trainer_wait_uploads(xf_trainer* tr) {
+  if (!tr) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaStreamSynchronize(tr->copy_stream));
+  return XF_OK;
+}

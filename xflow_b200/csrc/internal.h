@@ -1,0 +1,99 @@
+// Internal host-side structures shared by capi.cu / comm.cu / worker.cc.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/xflow_b200.h"
+#include "kernels.h"
+#include "table.cuh"
+
+void xf_set_error(const char* fmt, ...);
+
+#define XF_CUDA_TRY(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      xf_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                   cudaGetErrorString(_e));                                            \
+      return XF_ERR_CUDA;                                                              \
+    }                                                                                  \
+  } while (0)
+
+#define XF_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != XF_OK) return _r; \
+  } while (0)
+
+// growable device buffer
+struct XfDevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// growable pinned host buffer
+struct XfPinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct xf_table {
+  xf_table_config cfg;
+  XfTableView view;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  unsigned long long* d_size = nullptr;
+  int* d_error = nullptr;
+  uint64_t size_bound = 0;   // host-side upper bound on the number of live keys
+  uint64_t launches = 0;
+  // scratch for the host-pointer API
+  XfDevBuf s_keys, s_slots, s_w, s_v, s_nw, s_zw, s_nv, s_zv, s_present;
+
+  int alloc_table(uint64_t capacity);
+  int ensure_room(uint64_t incoming_keys);
+  int grow(uint64_t new_capacity);
+  int check_error();
+};
+
+struct XfBatchBuf {
+  XfDevBuf row_ptr, keys, labels;
+  XfPinBuf h_row_ptr, h_keys, h_labels;
+  cudaEvent_t copied = nullptr;   // H2D of this buffer finished (copy stream)
+  cudaEvent_t consumed = nullptr; // kernels reading this buffer finished (compute stream)
+  cudaEvent_t staged = nullptr;   // H2D out of the pinned staging finished
+};
+
+struct xf_trainer {
+  xf_table* table = nullptr;
+  xf_comm* comm = nullptr;
+  xf_trainer_config cfg;
+  cudaStream_t copy_stream = nullptr;
+  XfBatchBuf buf[2];
+  uint64_t step_index = 0;
+  XfDevBuf touched, loss, pctr;
+  unsigned int* d_touched_cnt = nullptr;
+  unsigned long long* d_unique_total = nullptr;
+  float* d_abs_loss = nullptr;          // 2 slots
+  float* h_abs_loss = nullptr;          // pinned, 2 slots
+  uint64_t n_steps = 0, n_rows = 0, n_nnz = 0;
+  uint32_t last_rows = 0;
+  uint64_t launches = 0;
+  void* mg = nullptr;                   // multi-GPU exchange state (comm.cu)
+};
+
+// multi-GPU pieces implemented in comm.cu
+int xf_mg_create(xf_trainer* tr);
+void xf_mg_destroy(xf_trainer* tr);
+int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys, const uint8_t* d_labels,
+               uint32_t rows, uint32_t nnz, int mode, float* d_abs_loss);
+int xf_comm_nranks(xf_comm* c);
+int xf_comm_rank(xf_comm* c);

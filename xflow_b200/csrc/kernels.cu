@@ -1,0 +1,605 @@
+// sm_100a kernels of the xflow hot path.  All of them are HBM / L2-latency bound integer+float work
+// on 32-byte table sectors (see table.cuh); there is no dense tile anywhere on this path (the
+// reference's FM term is a per-row scalar, fm_worker.cc:177-196), so no tensor-core code.
+//
+//   xf_k_fill               table initialisation (EMPTY keys, g = -0.0f)
+//   xf_k_step<FM,VEC>       FUSED worker step: CSR -> probe/insert -> gather w(,v) -> per-row
+//                           warp-segmented sums -> sigmoid -> residual -> per-key gradient accumulate
+//                           into the row (L2 atomics on the sector just loaded) -> "touched" list.
+//                           = LRWorker::update's pull + calculate_loss + calculate_gradient
+//                           (lr_worker.cc:121-177) / FMWorker's (fm_worker.cc:126-245) without the
+//                           sort/unique/merge-join: the table row itself is the per-key accumulator.
+//   xf_k_update<VEC,SLOTG>  optimizer step over a list of rows (FTRL ftrl.h:54-79,112-146 /
+//                           SGD sgd.h:46-59,90-103), gradient either from the row's accumulators
+//                           (fused step; divides by the slice row count) or from a pushed array.
+//   xf_k_probe              keys -> slot indices (insert or find)     } generic Pull / Push /
+//   xf_k_gather             slot rows -> w / v arrays                 } import / export pieces
+//   xf_k_import / xf_k_export
+//   xf_k_rehash             growth
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "table.cuh"
+
+namespace cg = cooperative_groups;
+
+// -------------------------------------------------------------------------------------------------
+// fill
+// -------------------------------------------------------------------------------------------------
+__global__ void xf_k_fill(uint8_t* base, uint64_t cap, uint32_t stride) {
+  // one thread per 16-byte chunk of the table
+  const uint64_t chunks_per_row = stride / 16;
+  const uint64_t total = cap * chunks_per_row;
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total;
+       c += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = c / chunks_per_row;
+    uint32_t q = (uint32_t)(c % chunks_per_row);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q == 0) { v.x = 0xFFFFFFFFu; v.y = 0xFFFFFFFFu; }
+    if (q == 1) { v.w = XF_NEG_ZERO_BITS; }
+    *reinterpret_cast<uint4*>(base + r * stride + (uint64_t)q * 16) = v;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// vector helpers for the latent blocks
+// -------------------------------------------------------------------------------------------------
+template <int VEC> struct XfVec;
+template <> struct XfVec<4> { typedef float4 T; };
+template <> struct XfVec<2> { typedef float2 T; };
+template <> struct XfVec<1> { typedef float T; };
+
+template <int VEC>
+__device__ __forceinline__ void xf_ldv(const float* p, float (&o)[VEC]) {
+  if (VEC == 4) { float4 t = __ldcg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1 % VEC] = t.y; o[2 % VEC] = t.z; o[3 % VEC] = t.w; }
+  else if (VEC == 2) { float2 t = __ldcg(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1 % VEC] = t.y; }
+  else { o[0] = __ldcg(p); }
+}
+template <int VEC>
+__device__ __forceinline__ void xf_stv(float* p, const float (&o)[VEC]) {
+  if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+  else if (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1 % VEC]);
+  else *p = o[0];
+}
+// vector reduction (no return) into global memory: one L2 atomic transaction per 8/16 bytes
+template <int VEC>
+__device__ __forceinline__ void xf_redv(float* p, const float (&o)[VEC]) {
+  if (VEC == 4) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(o[0]), "f"(o[1 % VEC]),
+                 "f"(o[2 % VEC]), "f"(o[3 % VEC])
+                 : "memory");
+  } else if (VEC == 2) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(o[0]), "f"(o[1 % VEC]) : "memory");
+  } else {
+    atomicAdd(p, o[0]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// fused worker step
+// -------------------------------------------------------------------------------------------------
+// One warp per row, lane per token.  Phase A: probe each token's key (inserting missing keys, as
+// the Pull would), read w from the row's first sector and, for FM, reduce the latent row to
+// (sum_k v, sum_k v^2).  Warp-segmented sums give wx (and S, Q), one lane-uniform sigmoid gives the
+// residual.  Phase B: every token adds its contribution to its key's accumulators with L2 atomics on
+// the sector it has just loaded; the lane that finds the untouched marker (-0.0f) in `g` appends the
+// slot to the batch's touched list, which the optimizer kernel consumes.
+//   mode: 0 = train, 1 = predict (no phase B; Pull still inserts, lr_worker.cc:47)
+#define XF_TOK_CACHE 4  // tokens per lane whose slot index is kept in registers (rows <= 128 tokens)
+
+template <bool FM, int VEC>
+__global__ void __launch_bounds__(256)
+xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* __restrict__ keys,
+          const uint8_t* __restrict__ labels, int B, int mode, uint32_t* __restrict__ touched,
+          unsigned int* __restrict__ touched_cnt, float* __restrict__ loss_out, float* __restrict__ pctr_out,
+          float* __restrict__ abs_loss_sum) {
+  __shared__ float s_abs[8];
+  float abs_acc = 0.f;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * warps_per_block;
+  const int K = t.K;
+
+  for (int row = gwarp; row < B; row += nwarps) {
+    const uint32_t beg = __ldg(row_ptr + row);
+    const uint32_t end = __ldg(row_ptr + row + 1);
+    const int iters = (int)((end - beg + 31u) >> 5);
+
+    float wsum = 0.f, ssum = 0.f, qsum = 0.f;
+    int64_t slot_c[XF_TOK_CACHE];
+#pragma unroll
+    for (int c = 0; c < XF_TOK_CACHE; ++c) slot_c[c] = -1;
+
+    // ---------------- phase A
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t j = beg + (uint32_t)it * 32u + (uint32_t)lane;
+      int64_t s = -1;
+      if (j < end) {
+        const uint64_t key = __ldg(keys + j);
+        XfHead h;
+        s = xf_probe<true>(t, key, &h);
+        if (s >= 0) {
+          wsum += h.w;
+          if (FM) {
+            const uint8_t* rowp = xf_row(t, (uint64_t)s);
+            const float* vp = reinterpret_cast<const float*>(rowp + 32);
+            float st = 0.f, qt = 0.f;
+            if (h.flags & XF_FLAG_V_READY) {
+              for (int k = 0; k < K; k += VEC) {
+                float v[VEC];
+                xf_ldv<VEC>(vp + k, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { st += v[e]; qt = __fadd_rn(qt, __fmul_rn(v[e], v[e])); }
+              }
+            } else {
+              for (int k = 0; k < K; ++k) {
+                float v = xf_v_init(t, key, (uint32_t)k);
+                st += v;
+                qt = __fadd_rn(qt, __fmul_rn(v, v));
+              }
+            }
+            ssum += st;
+            qsum += qt;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < XF_TOK_CACHE; ++c)
+        if (it == c) slot_c[c] = s;
+    }
+
+    // ---------------- per-row reduction, sigmoid, residual
+    const float wx = xf_warp_sum(wsum);
+    float S = 0.f, arg = wx;
+    if (FM) {
+      S = xf_warp_sum(ssum);
+      const float Q = xf_warp_sum(qsum);
+      const float v_y = __fsub_rn(__fmul_rn(S, S), Q);  // fm_worker.cc:193-196
+      arg = __fadd_rn(wx, v_y);
+    }
+    const float pctr = xf_sigmoid(arg);
+    if (mode == 1) {
+      if (lane == 0 && pctr_out) pctr_out[row] = pctr;
+      continue;
+    }
+    const float loss = __fsub_rn(pctr, (float)labels[row]);  // lr_worker.cc:141 ; fm_worker.cc:200
+    if (lane == 0 && loss_out) loss_out[row] = loss;
+    abs_acc += fabsf(loss);
+
+    // ---------------- phase B
+    float gw_c = loss;
+    if (FM) {
+      // fm_worker.cc:140 accumulates the w-gradient inside the k loop: K sequential float adds
+      gw_c = 0.f;
+      for (int k = 0; k < K; ++k) gw_c += loss;
+    }
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t j = beg + (uint32_t)it * 32u + (uint32_t)lane;
+      int64_t s = -1;
+      if (it < XF_TOK_CACHE) {
+#pragma unroll
+        for (int c = 0; c < XF_TOK_CACHE; ++c)
+          if (it == c) s = slot_c[c];
+      } else if (j < end) {
+        XfHead h;
+        s = xf_probe<false>(t, __ldg(keys + j), &h);
+      }
+      bool first = false;
+      if (s >= 0) {
+        uint8_t* rowp = xf_row(t, (uint64_t)s);
+        const float old = atomicAdd(xf_row_g(rowp), gw_c);
+        first = (__float_as_uint(old) == XF_NEG_ZERO_BITS);
+        if (FM) {
+          const float* vp = xf_row_v(rowp);
+          float* gvp = xf_row_gv(rowp, K);
+          const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + 8));
+          const bool ready = (flags & XF_FLAG_V_READY) != 0;
+          const uint64_t key = ready ? 0ull : __ldg(keys + j);
+          for (int k = 0; k < K; k += VEC) {
+            float v[VEC], gc[VEC];
+            if (ready) {
+              xf_ldv<VEC>(vp + k, v);
+            } else {
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) v[e] = xf_v_init(t, key, (uint32_t)(k + e));
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) gc[e] = __fmul_rn(loss, __fsub_rn(S, v[e]));  // fm_worker.cc:141-142
+            xf_redv<VEC>(gvp + k, gc);
+          }
+        }
+      }
+      // warp-aggregated append of first-touched slots
+      const unsigned m = __ballot_sync(0xffffffffu, first);
+      if (m) {
+        unsigned base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(touched_cnt, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (first) touched[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)s;
+      }
+    }
+  }
+  // monitoring scalar: sum over rows of |pctr - label| (one atomic per block)
+  if (abs_loss_sum != nullptr && mode == 0) {
+    if (lane == 0) s_abs[threadIdx.x >> 5] = abs_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_abs[w];
+      atomicAdd(abs_loss_sum, tot);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// optimizer step over a list of rows
+// -------------------------------------------------------------------------------------------------
+// TPS (power of two <= 32) consecutive lanes own one row: lane q handles latent coordinates
+// [q*VEC, q*VEC+VEC) and lane 0 additionally the scalar w coordinate.
+//   SLOTG = true : gradients are the row's own accumulators (fused step).  g <- g / rows, then the
+//                  accumulators are reset (g = -0.0f marker, gv = 0).
+//   SLOTG = false: gradients come from gw[i] / gv[i*K+k] (Push).  part bit0: apply w, bit1: apply v.
+template <int VEC, bool SLOTG>
+__global__ void __launch_bounds__(256)
+xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, const unsigned int* __restrict__ n_ptr,
+            uint64_t n_fixed, int tps, double rows, const float* __restrict__ gw,
+            const float* __restrict__ gv, int part) {
+  const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_fixed;
+  const int K = t.K;
+  const uint64_t gthread = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  const int q = (int)(threadIdx.x & (unsigned)(tps - 1));
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (tps == 32) ? 0xffffffffu : (((1u << tps) - 1u) << (lane & ~(unsigned)(tps - 1)));
+  const uint64_t n_round = (n * (uint64_t)tps + nthreads - 1) / nthreads * nthreads;  // keep groups converged
+
+  for (uint64_t x = gthread; x < n_round; x += nthreads) {
+    const uint64_t i = x / (uint64_t)tps;
+    const bool live = i < n;
+    uint8_t* rowp = nullptr;
+    uint32_t flags = 0;
+    uint64_t key = 0;
+    if (live) {
+      const uint32_t s = slots[i];
+      if (s != 0xFFFFFFFFu) {
+        rowp = xf_row(t, s);
+        uint4 a = __ldcg(reinterpret_cast<const uint4*>(rowp));
+        key = (uint64_t)a.x | ((uint64_t)a.y << 32);
+        flags = a.z;
+      }
+    }
+    __syncwarp(group_mask);  // every lane of the group has read `flags` before lane 0 rewrites it
+    if (rowp == nullptr) continue;
+
+    if (q == 0 && (part & 1)) {
+      float4 b = __ldcg(reinterpret_cast<const float4*>(rowp + 16));
+      float g = SLOTG ? xf_div_rows(b.w, rows) : gw[i];
+      xf_opt_coord(t, g, b.x, b.y, b.z);
+      if (SLOTG) b.w = -0.0f;
+      *reinterpret_cast<float4*>(rowp + 16) = b;
+    }
+    if (K > 0 && (part & 2)) {
+      const bool ready = (flags & XF_FLAG_V_READY) != 0;
+      float* vp = xf_row_v(rowp);
+      float* gvp = xf_row_gv(rowp, K);
+      float* nvp = xf_row_nv(rowp, K);
+      float* zvp = xf_row_zv(rowp, K);
+      const int nchunk = K / VEC;
+      for (int c = q; c < nchunk; c += tps) {
+        const int k = c * VEC;
+        float v[VEC], g[VEC], nn[VEC], zz[VEC];
+        if (ready) {
+          xf_ldv<VEC>(vp + k, v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) v[e] = xf_v_init(t, key, (uint32_t)(k + e));
+        }
+        if (SLOTG) {
+          xf_ldv<VEC>(gvp + k, g);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) g[e] = xf_div_rows(g[e], rows);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) g[e] = gv[i * (uint64_t)K + k + e];
+        }
+        if (t.opt == XF_OPT_FTRL) {
+          if (ready) { xf_ldv<VEC>(nvp + k, nn); xf_ldv<VEC>(zvp + k, zz); }
+          else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { nn[e] = 0.f; zz[e] = 0.f; }
+          }
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) xf_ftrl_coord(t, g[e], v[e], nn[e], zz[e]);
+          xf_stv<VEC>(nvp + k, nn);
+          xf_stv<VEC>(zvp + k, zz);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) xf_sgd_coord(t, g[e], v[e]);
+        }
+        xf_stv<VEC>(vp + k, v);
+        if (SLOTG) {
+          float zero[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) zero[e] = 0.f;
+          xf_stv<VEC>(gvp + k, zero);
+        }
+      }
+      if (q == 0 && !ready) *reinterpret_cast<uint32_t*>(rowp + 8) = flags | XF_FLAG_V_READY;
+    }
+  }
+}
+
+// bookkeeping between batches: fold the touched count into the running total, clear the counter
+__global__ void xf_k_batch_end(unsigned int* touched_cnt, unsigned long long* unique_total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    *unique_total += (unsigned long long)*touched_cnt;
+    *touched_cnt = 0;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// generic pieces: Pull / Push / import / export / growth
+// -------------------------------------------------------------------------------------------------
+// keys -> slots (0xFFFFFFFF = absent / overflow).  Optionally emits w (app-0 Pull, ftrl.h:75-77).
+template <bool INSERT>
+__global__ void xf_k_probe(XfTableView t, const uint64_t* __restrict__ keys, uint64_t n,
+                           uint32_t* __restrict__ slots, float* __restrict__ w_out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    XfHead h;
+    h.w = 0.f;
+    int64_t s = xf_probe<INSERT>(t, keys[i], &h);
+    slots[i] = s >= 0 ? (uint32_t)s : 0xFFFFFFFFu;
+    if (w_out) w_out[i] = s >= 0 ? h.w : 0.f;
+  }
+}
+
+// latent rows of `slots` -> v_out[n*K] (app-1 Pull, ftrl.h:142-144); one thread per coordinate
+__global__ void xf_k_gather_v(XfTableView t, const uint32_t* __restrict__ slots, const uint64_t* __restrict__ keys,
+                              uint64_t n, float* __restrict__ v_out) {
+  const int K = t.K;
+  const uint64_t total = n * (uint64_t)K;
+  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total;
+       x += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = x / K;
+    const int k = (int)(x % K);
+    const uint32_t s = slots[i];
+    float v = 0.f;
+    if (s != 0xFFFFFFFFu) {
+      const uint8_t* rowp = xf_row(t, s);
+      const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + 8));
+      v = (flags & XF_FLAG_V_READY) ? __ldcg(reinterpret_cast<const float*>(rowp + 32) + k)
+                                    : xf_v_init(t, keys[i], (uint32_t)k);
+    }
+    v_out[x] = v;
+  }
+}
+
+// overwrite rows (replay of an exported table).  Keys must be unique; slots from xf_k_probe<true>.
+__global__ void xf_k_import(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n,
+                            const float* w, const float* nw, const float* zw, const float* v,
+                            const float* nv, const float* zv) {
+  const int K = t.K;
+  const uint64_t per = (uint64_t)K + 1;
+  const uint64_t total = n * per;
+  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total;
+       x += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = x / per;
+    const int c = (int)(x % per);
+    const uint32_t s = slots[i];
+    if (s == 0xFFFFFFFFu) continue;
+    uint8_t* rowp = xf_row(t, s);
+    if (c == 0) {
+      if (w) {
+        float4 b = make_float4(w[i], nw ? nw[i] : 0.f, zw ? zw[i] : 0.f, -0.0f);
+        *reinterpret_cast<float4*>(rowp + 16) = b;
+      }
+      if (v && K > 0) *reinterpret_cast<uint32_t*>(rowp + 8) = XF_FLAG_V_READY;
+    } else if (v) {
+      const int k = c - 1;
+      xf_row_v(rowp)[k] = v[i * K + k];
+      xf_row_gv(rowp, K)[k] = 0.f;
+      if (t.opt == XF_OPT_FTRL) {
+        xf_row_nv(rowp, K)[k] = nv ? nv[i * K + k] : 0.f;
+        xf_row_zv(rowp, K)[k] = zv ? zv[i * K + k] : 0.f;
+      }
+    }
+  }
+}
+
+// read rows without inserting; slots from xf_k_probe<false>
+__global__ void xf_k_export(XfTableView t, const uint32_t* __restrict__ slots, const uint64_t* __restrict__ keys,
+                            uint64_t n, float* w, float* nw, float* zw, float* v, float* nv, float* zv,
+                            uint8_t* present) {
+  const int K = t.K;
+  const uint64_t per = (uint64_t)K + 1;
+  const uint64_t total = n * per;
+  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total;
+       x += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = x / per;
+    const int c = (int)(x % per);
+    const uint32_t s = slots[i];
+    const bool have = s != 0xFFFFFFFFu;
+    const uint8_t* rowp = have ? xf_row(t, s) : nullptr;
+    if (c == 0) {
+      float4 b = have ? __ldcg(reinterpret_cast<const float4*>(rowp + 16)) : make_float4(0, 0, 0, 0);
+      if (present) present[i] = have ? 1 : 0;
+      if (w) w[i] = b.x;
+      if (nw) nw[i] = b.y;
+      if (zw) zw[i] = b.z;
+    } else if (v) {
+      const int k = c - 1;
+      float vv = 0.f, nn = 0.f, zz = 0.f;
+      if (have) {
+        const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + 8));
+        if (flags & XF_FLAG_V_READY) {
+          vv = __ldcg(reinterpret_cast<const float*>(rowp + 32) + k);
+          if (t.opt == XF_OPT_FTRL) {
+            nn = __ldcg(reinterpret_cast<const float*>(rowp + 32) + 2 * K + k);
+            zz = __ldcg(reinterpret_cast<const float*>(rowp + 32) + 3 * K + k);
+          }
+        } else {
+          vv = xf_v_init(t, keys[i], (uint32_t)k);
+        }
+      }
+      v[i * K + k] = vv;
+      if (nv) nv[i * K + k] = nn;
+      if (zv) zv[i * K + k] = zz;
+    }
+  }
+}
+
+// growth: re-insert every live row of `src` into the (larger, freshly filled) `dst`
+__global__ void xf_k_rehash(XfTableView src, XfTableView dst) {
+  const uint64_t cap = src.mask + 1;
+  const uint32_t chunks = src.stride / 16;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < cap;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t* srow = xf_row(src, r);
+    uint4 a = *reinterpret_cast<const uint4*>(srow);
+    uint64_t key = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    if (key == XF_EMPTY_KEY) continue;
+    XfHead h;
+    int64_t s = xf_probe<true>(dst, key, &h);
+    if (s < 0) continue;
+    uint8_t* drow = xf_row(dst, (uint64_t)s);
+    // the key word is already in place (CAS); copy flags and everything after
+    *reinterpret_cast<uint2*>(drow + 8) = make_uint2(a.z, a.w);
+    for (uint32_t c = 1; c < chunks; ++c)
+      *reinterpret_cast<uint4*>(drow + 16 * c) = *reinterpret_cast<const uint4*>(srow + 16 * c);
+  }
+}
+
+// list every live key (checkpoint / full export)
+__global__ void xf_k_list_keys(XfTableView t, uint64_t* keys_out, unsigned long long* count, uint64_t max_out) {
+  const uint64_t cap = t.mask + 1;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < cap;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = *reinterpret_cast<const uint64_t*>(xf_row(t, r));
+    if (key == XF_EMPTY_KEY) continue;
+    unsigned long long idx = atomicAdd(count, 1ull);
+    if (idx < max_out) keys_out[idx] = key;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-side launchers (plain C++ signatures, see kernels.h)
+// -------------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int xf_sms() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+static inline int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm) {
+  uint64_t want = (work_items + block - 1) / block;
+  uint64_t cap = (uint64_t)xf_sms() * blocks_per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+int xf_vec_for(int K) { return K <= 0 ? 1 : (K % 4 == 0 ? 4 : (K % 2 == 0 ? 2 : 1)); }
+int xf_tps_for(int K) {
+  if (K <= 0) return 1;
+  int chunks = K / xf_vec_for(K);
+  int tps = 1;
+  while (tps < chunks && tps < 32) tps <<= 1;
+  return tps;
+}
+
+void xf_launch_fill(const XfTableView& t, cudaStream_t st) {
+  uint64_t cap = t.mask + 1;
+  uint64_t total = cap * (t.stride / 16);
+  xf_k_fill<<<xf_grid_for(total, 256, 16), 256, 0, st>>>(t.base, cap, t.stride);
+}
+
+void xf_launch_step(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* labels,
+                    int B, int mode, uint32_t* touched, unsigned int* touched_cnt, float* loss_out,
+                    float* pctr_out, float* abs_loss_sum, cudaStream_t st) {
+  if (B <= 0) return;
+  const int block = 256;
+  const int grid = xf_grid_for((uint64_t)B * 32, block, 8);
+  if (t.K == 0) {
+    xf_k_step<false, 1><<<grid, block, 0, st>>>(t, row_ptr, keys, labels, B, mode, touched, touched_cnt,
+                                                  loss_out, pctr_out, abs_loss_sum);
+  } else {
+    switch (xf_vec_for(t.K)) {
+      case 4: xf_k_step<true, 4><<<grid, block, 0, st>>>(t, row_ptr, keys, labels, B, mode, touched, touched_cnt, loss_out, pctr_out, abs_loss_sum); break;
+      case 2: xf_k_step<true, 2><<<grid, block, 0, st>>>(t, row_ptr, keys, labels, B, mode, touched, touched_cnt, loss_out, pctr_out, abs_loss_sum); break;
+      default: xf_k_step<true, 1><<<grid, block, 0, st>>>(t, row_ptr, keys, labels, B, mode, touched, touched_cnt, loss_out, pctr_out, abs_loss_sum); break;
+    }
+  }
+}
+
+template <bool SLOTG>
+static void xf_launch_update_t(const XfTableView& t, const uint32_t* slots, const unsigned int* n_ptr,
+                               uint64_t n_fixed, uint64_t n_max, double rows, const float* gw, const float* gv,
+                               int part, cudaStream_t st) {
+  const int tps = xf_tps_for(t.K);
+  const int grid = xf_grid_for(n_max * (uint64_t)tps, 256, 8);
+  switch (xf_vec_for(t.K)) {
+    case 4: xf_k_update<4, SLOTG><<<grid, 256, 0, st>>>(t, slots, n_ptr, n_fixed, tps, rows, gw, gv, part); break;
+    case 2: xf_k_update<2, SLOTG><<<grid, 256, 0, st>>>(t, slots, n_ptr, n_fixed, tps, rows, gw, gv, part); break;
+    default: xf_k_update<1, SLOTG><<<grid, 256, 0, st>>>(t, slots, n_ptr, n_fixed, tps, rows, gw, gv, part); break;
+  }
+}
+
+void xf_launch_update_touched(const XfTableView& t, const uint32_t* touched, const unsigned int* touched_cnt,
+                              uint64_t n_max, double rows, cudaStream_t st) {
+  if (n_max == 0) return;
+  xf_launch_update_t<true>(t, touched, touched_cnt, 0, n_max, rows, nullptr, nullptr, 3, st);
+}
+
+void xf_launch_update_pushed(const XfTableView& t, const uint32_t* slots, uint64_t n, const float* gw,
+                             const float* gv, cudaStream_t st) {
+  if (n == 0) return;
+  int part = (gw ? 1 : 0) | (gv ? 2 : 0);
+  xf_launch_update_t<false>(t, slots, nullptr, n, n, 1.0, gw, gv, part, st);
+}
+
+void xf_launch_batch_end(unsigned int* touched_cnt, unsigned long long* unique_total, cudaStream_t st) {
+  xf_k_batch_end<<<1, 32, 0, st>>>(touched_cnt, unique_total);
+}
+
+void xf_launch_probe(const XfTableView& t, const uint64_t* keys, uint64_t n, bool insert, uint32_t* slots,
+                     float* w_out, cudaStream_t st) {
+  if (n == 0) return;
+  const int grid = xf_grid_for(n, 256, 8);
+  if (insert) xf_k_probe<true><<<grid, 256, 0, st>>>(t, keys, n, slots, w_out);
+  else xf_k_probe<false><<<grid, 256, 0, st>>>(t, keys, n, slots, w_out);
+}
+
+void xf_launch_gather_v(const XfTableView& t, const uint32_t* slots, const uint64_t* keys, uint64_t n,
+                        float* v_out, cudaStream_t st) {
+  if (n == 0 || t.K == 0) return;
+  xf_k_gather_v<<<xf_grid_for(n * t.K, 256, 8), 256, 0, st>>>(t, slots, keys, n, v_out);
+}
+
+void xf_launch_import(const XfTableView& t, const uint32_t* slots, uint64_t n, const float* w, const float* nw,
+                      const float* zw, const float* v, const float* nv, const float* zv, cudaStream_t st) {
+  if (n == 0) return;
+  xf_k_import<<<xf_grid_for(n * (t.K + 1), 256, 8), 256, 0, st>>>(t, slots, n, w, nw, zw, v, nv, zv);
+}
+
+void xf_launch_export(const XfTableView& t, const uint32_t* slots, const uint64_t* keys, uint64_t n, float* w,
+                      float* nw, float* zw, float* v, float* nv, float* zv, uint8_t* present, cudaStream_t st) {
+  if (n == 0) return;
+  xf_k_export<<<xf_grid_for(n * (t.K + 1), 256, 8), 256, 0, st>>>(t, slots, keys, n, w, nw, zw, v, nv, zv, present);
+}
+
+void xf_launch_rehash(const XfTableView& src, const XfTableView& dst, cudaStream_t st) {
+  xf_k_rehash<<<xf_grid_for(src.mask + 1, 256, 8), 256, 0, st>>>(src, dst);
+}
+
+void xf_launch_list_keys(const XfTableView& t, uint64_t* keys_out, unsigned long long* count, uint64_t max_out,
+                         cudaStream_t st) {
+  xf_k_list_keys<<<xf_grid_for(t.mask + 1, 256, 8), 256, 0, st>>>(t, keys_out, count, max_out);
+}

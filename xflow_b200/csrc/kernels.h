@@ -1,0 +1,30 @@
+// Host-callable launchers of kernels.cu (internal; the public surface is include/xflow_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "table.cuh"
+
+int xf_vec_for(int K);
+int xf_tps_for(int K);
+
+void xf_launch_fill(const XfTableView& t, cudaStream_t st);
+void xf_launch_step(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* labels,
+                    int B, int mode, uint32_t* touched, unsigned int* touched_cnt, float* loss_out,
+                    float* pctr_out, float* abs_loss_sum, cudaStream_t st);
+void xf_launch_update_touched(const XfTableView& t, const uint32_t* touched, const unsigned int* touched_cnt,
+                              uint64_t n_max, double rows, cudaStream_t st);
+void xf_launch_update_pushed(const XfTableView& t, const uint32_t* slots, uint64_t n, const float* gw,
+                             const float* gv, cudaStream_t st);
+void xf_launch_batch_end(unsigned int* touched_cnt, unsigned long long* unique_total, cudaStream_t st);
+void xf_launch_probe(const XfTableView& t, const uint64_t* keys, uint64_t n, bool insert, uint32_t* slots,
+                     float* w_out, cudaStream_t st);
+void xf_launch_gather_v(const XfTableView& t, const uint32_t* slots, const uint64_t* keys, uint64_t n,
+                        float* v_out, cudaStream_t st);
+void xf_launch_import(const XfTableView& t, const uint32_t* slots, uint64_t n, const float* w, const float* nw,
+                      const float* zw, const float* v, const float* nv, const float* zv, cudaStream_t st);
+void xf_launch_export(const XfTableView& t, const uint32_t* slots, const uint64_t* keys, uint64_t n, float* w,
+                      float* nw, float* zw, float* v, float* nv, float* zv, uint8_t* present, cudaStream_t st);
+void xf_launch_rehash(const XfTableView& src, const XfTableView& dst, cudaStream_t st);
+void xf_launch_list_keys(const XfTableView& t, uint64_t* keys_out, unsigned long long* count, uint64_t max_out,
+                         cudaStream_t st);

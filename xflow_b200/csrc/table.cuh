@@ -1,0 +1,208 @@
+// Device-side layout and primitives of the GPU-resident parameter table.
+//
+// The table replaces the reference's server-side state — the two
+// std::unordered_map<ps::Key, FTRLEntry/SGDEntry> stores behind KV apps 0 (w) and 1 (v)
+// (src/optimizer/ftrl.h:27-36,84,87-96,151 ; src/optimizer/sgd.h:23-28,61,67-72,105) —
+// with ONE open-addressing hash table in HBM whose row holds everything a key owns:
+//
+//   byte  0  u64  key            (EMPTY = 2^64-1; never a legal key in the reference either:
+//                                 it lies outside every server range, postoffice.cc:134-143)
+//   byte  8  u32  flags          bit0 = latent block materialised (V_READY)
+//   byte 12  u32  reserved
+//   byte 16  f32  w              app-0 weight                         (FTRLEntry_w::w / SGDEntry_w::w)
+//   byte 20  f32  n              FTRL accumulator of w (unused by SGD)
+//   byte 24  f32  z              FTRL accumulator of w (unused by SGD)
+//   byte 28  f32  g              per-batch gradient accumulator of w; -0.0f == "untouched this batch"
+//   ---- 32 B = one DRAM sector: an LR pull, gradient accumulate or update touches exactly one ----
+//   byte 32            f32 v[K]    app-1 latent row
+//   byte 32 +   4K     f32 gv[K]   per-batch gradient accumulator of v
+//   byte 32 +   8K     f32 nv[K]   (FTRL only)
+//   byte 32 +  12K     f32 zv[K]   (FTRL only)
+//   row stride = round_up(32 + nblk*4K, 32), nblk = 4 (FTRL) / 2 (SGD).
+//
+// Missing keys are inserted on first touch by a pull OR a push, like `store[key]`
+// (ftrl.h:56,114-120 ; sgd.h:48,92).  Default contents: w = n = z = 0 ; v per init mode.  The latent
+// block is materialised lazily by the first update of the key (a row is only ever written by
+// kernels that own the key exclusively); until then readers compute the same deterministic
+// initial value from (key, k, seed), so "insert on pull" is observably identical.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XF_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define XF_FLAG_V_READY 1u
+#define XF_NEG_ZERO_BITS 0x80000000u
+#define XF_MAX_PROBE 8192
+
+enum { XF_OPT_FTRL = 0, XF_OPT_SGD = 1 };
+enum { XF_INIT_DEFAULT = 0, XF_INIT_COUNTER = 1, XF_INIT_ZERO = 3 };
+
+struct XfTableView {
+  uint8_t* base;
+  uint64_t mask;      // capacity - 1
+  uint32_t log2cap;
+  uint32_t stride;    // bytes per row
+  int K;
+  int opt;
+  int v_init;         // resolved: 0 const(v_const), 1 counter normal, 3 zero
+  float v_const;
+  uint64_t seed;
+  float alpha, beta, lambda1, lambda2, learning_rate;
+  unsigned long long* size;   // number of keys present
+  int* error;                 // set to 1 when a probe sequence overflows (table full)
+};
+
+__host__ __device__ inline uint32_t xf_row_stride(int K, int opt) {
+  uint32_t nblk = (opt == XF_OPT_FTRL) ? 4u : 2u;
+  uint32_t bytes = 32u + nblk * 4u * (uint32_t)K;
+  return (bytes + 31u) & ~31u;
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint64_t xf_slot_hash(uint64_t key, uint32_t log2cap) {
+  return (key * 0x9E3779B97F4A7C15ull) >> (64 - log2cap);
+}
+
+// ---- counter-based initial value of the latent table; must stay bit-identical to
+// ---- oracle/xflow_oracle.cc: xo_counter_normal (integer ops + two exactly rounded float ops)
+__host__ __device__ __forceinline__ uint64_t xf_splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ float xf_counter_normal(uint64_t key, uint32_t k, uint64_t seed) {
+  uint64_t base = xf_splitmix64(key ^ xf_splitmix64(seed + 0x632BE59BD9B4E019ull * (uint64_t)(k + 1)));
+  uint32_t sum = 0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    uint64_t x = xf_splitmix64(base + (uint64_t)r);
+    sum += (uint32_t)(x & 0xFFFF) + (uint32_t)((x >> 16) & 0xFFFF) + (uint32_t)((x >> 32) & 0xFFFF) +
+           (uint32_t)((x >> 48) & 0xFFFF);
+  }
+  float u = __fmul_rn((float)((int32_t)sum - 6 * 65535), 1.0f / 65536.0f);
+  return __fmul_rn(u, 1e-2f);
+}
+__device__ __forceinline__ float xf_v_init(const XfTableView& t, uint64_t key, uint32_t k) {
+  if (t.v_init == XF_INIT_COUNTER) return xf_counter_normal(key, k, t.seed);
+  if (t.v_init == XF_INIT_ZERO) return 0.0f;
+  return t.v_const;
+}
+
+// ---- row accessors
+__device__ __forceinline__ uint8_t* xf_row(const XfTableView& t, uint64_t slot) {
+  return t.base + slot * (uint64_t)t.stride;
+}
+__device__ __forceinline__ float* xf_row_g(uint8_t* row) { return reinterpret_cast<float*>(row + 28); }
+__device__ __forceinline__ float* xf_row_v(uint8_t* row) { return reinterpret_cast<float*>(row + 32); }
+__device__ __forceinline__ float* xf_row_gv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + 32) + K; }
+__device__ __forceinline__ float* xf_row_nv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + 32) + 2 * K; }
+__device__ __forceinline__ float* xf_row_zv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + 32) + 3 * K; }
+
+struct XfHead {
+  uint64_t key;
+  uint32_t flags;
+  float w, n, z, g;
+};
+
+__device__ __forceinline__ XfHead xf_load_head(const uint8_t* row) {
+  // one 32-byte sector, two 16-byte L2 loads (L1 is useless for random rows)
+  uint4 a = __ldcg(reinterpret_cast<const uint4*>(row));
+  float4 b = __ldcg(reinterpret_cast<const float4*>(row + 16));
+  XfHead h;
+  h.key = (uint64_t)a.x | ((uint64_t)a.y << 32);
+  h.flags = a.z;
+  h.w = b.x; h.n = b.y; h.z = b.z; h.g = b.w;
+  return h;
+}
+
+// Find `key`; if INSERT, claim an empty slot for it when absent (store[key] semantics).
+// Returns the slot index, or -1 (not found without INSERT, or probe overflow -> *t.error = 1).
+// `head` receives the row's first sector as it was when the key matched (or defaults on insert).
+template <bool INSERT>
+__device__ __forceinline__ int64_t xf_probe(const XfTableView& t, uint64_t key, XfHead* head) {
+  uint64_t s = xf_slot_hash(key, t.log2cap);
+  for (int probes = 0; probes < XF_MAX_PROBE; ++probes) {
+    uint8_t* row = xf_row(t, s);
+    XfHead h = xf_load_head(row);
+    if (h.key == key) {
+      *head = h;
+      return (int64_t)s;
+    }
+    if (h.key == XF_EMPTY_KEY) {
+      if (!INSERT) return -1;
+      unsigned long long old =
+          atomicCAS(reinterpret_cast<unsigned long long*>(row), (unsigned long long)XF_EMPTY_KEY,
+                    (unsigned long long)key);
+      if (old == XF_EMPTY_KEY) {
+        // we created the entry: count it (warp-aggregated) and report default contents
+        unsigned m = __activemask();
+        int leader = __ffs(m) - 1;
+        if ((int)(threadIdx.x & 31) == leader) atomicAdd(t.size, (unsigned long long)__popc(m));
+        h.key = key; h.flags = 0; h.w = 0.f; h.n = 0.f; h.z = 0.f; h.g = -0.0f;
+        *head = h;
+        return (int64_t)s;
+      }
+      if (old == key) {
+        // raced with another inserter of the same key: the parameter fields are still defaults
+        h.key = key;
+        *head = h;
+        return (int64_t)s;
+      }
+      // a different key took the slot: fall through to the next one
+    }
+    s = (s + 1) & t.mask;
+  }
+  *t.error = 1;
+  return -1;
+}
+
+// ---- arithmetic restated from the reference, IEEE-rounded op by op (no FMA contraction) ----
+
+// Base::sigmoid  src/base/base.h:54-63
+__device__ __forceinline__ float xf_sigmoid(float x) {
+  if (x < -30.f) return (float)1e-6;
+  if (x > 30.f) return 1.0f;
+  double ex = pow(2.718281828, (double)x);
+  return (float)(ex / (1.0 + ex));
+}
+
+// FTRL-proximal coordinate update  src/optimizer/ftrl.h:59-74 (== :126-141)
+__device__ __forceinline__ void xf_ftrl_coord(const XfTableView& t, float g, float& w, float& n, float& z) {
+  float old_n = n;
+  float nn = __fadd_rn(old_n, __fmul_rn(g, g));
+  float sig = __fdiv_rn(__fsub_rn(__fsqrt_rn(nn), __fsqrt_rn(old_n)), t.alpha);
+  z = __fadd_rn(z, __fsub_rn(g, __fmul_rn(sig, w)));
+  n = nn;
+  if (fabsf(z) <= t.lambda1) {
+    w = 0.0f;
+  } else {
+    float tmpr = 0.0f;
+    if (z > 0.0f) tmpr = __fsub_rn(z, t.lambda1);
+    if (z < 0.0f) tmpr = __fadd_rn(z, t.lambda1);
+    float tmpl = -__fadd_rn(__fdiv_rn(__fadd_rn(t.beta, __fsqrt_rn(n)), t.alpha), t.lambda2);
+    w = __fdiv_rn(tmpr, tmpl);
+  }
+}
+
+// SGD coordinate update  src/optimizer/sgd.h:52,96
+__device__ __forceinline__ void xf_sgd_coord(const XfTableView& t, float g, float& w) {
+  w = __fsub_rn(w, __fmul_rn(t.learning_rate, g));
+}
+
+__device__ __forceinline__ void xf_opt_coord(const XfTableView& t, float g, float& w, float& n, float& z) {
+  if (t.opt == XF_OPT_FTRL) xf_ftrl_coord(t, g, w, n, z);
+  else xf_sgd_coord(t, g, w);
+}
+
+// push_gradient[i] /= 1.0 * loss.size()  lr_worker.cc:116-118 ; fm_worker.cc:150-156 (double divide)
+__device__ __forceinline__ float xf_div_rows(float g, double rows) { return (float)((double)g / rows); }
+
+__device__ __forceinline__ float xf_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+#endif  // __CUDACC__

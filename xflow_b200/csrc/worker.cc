@@ -1,0 +1,328 @@
+// C ABI layer 1 and the C++ model/optimizer surface (include/xflow/xflow.h): the reference's
+// LRWorker / FMWorker / Server call flow, re-hosted on the device table and the fused step.
+// Host orchestration only; all arithmetic of the hot path runs in kernels.cu.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <functional>
+#include <iostream>
+#include <mutex>
+#include <stdexcept>
+
+#include "../../include/xflow/xflow.h"
+
+void xf_set_error(const char* fmt, ...);
+
+namespace xflow {
+
+int w_dim = 1;                // ftrl.h:15
+int v_dim = 10;               // ftrl.h:16
+float alpha = 5e-2;           // ftrl.h:17
+float beta = 1.0;             // ftrl.h:18
+float lambda1 = 5e-5;         // ftrl.h:19
+float lambda2 = 10.0;         // ftrl.h:20
+float learning_rate = 0.001;  // sgd.h:16
+
+namespace {
+std::mutex g_mu;
+Server* g_server = nullptr;
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// errors from the C ABI surface as exceptions inside the C++ façade (the reference's CHECK ->
+// LOG(FATAL) -> throw dmlc::Error convention, dmlc/logging.h:183-209); XF* entry points catch them.
+void must(int rc, const char* what) {
+  if (rc != XF_OK) throw std::runtime_error(std::string(what) + ": " + xf_last_error());
+}
+}  // namespace
+
+int MyRank() { return env_int("XFLOW_RANK", env_int("RANK", 0)); }
+
+// ------------------------------------------------------------------------------------------------
+// Server  (src/model/server.h:20-35)
+// ------------------------------------------------------------------------------------------------
+Server::Server(Optimizer opt, int latent_dim, int device)
+    : opt_(opt), latent_dim_(latent_dim), device_(device < 0 ? env_int("XFLOW_DEVICE", 0) : device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_server) g_server = this;
+  std::cout << "init server success " << std::endl;  // server.h:30
+}
+
+Server::~Server() {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_server == this) g_server = nullptr;
+  }
+  if (lr_) xf_table_destroy(lr_);
+  if (fm_) xf_table_destroy(fm_);
+}
+
+Server* Server::Get() {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_server) return g_server;
+  }
+  Optimizer opt = Optimizer::FTRL;
+  const char* o = getenv("XFLOW_OPTIMIZER");
+  if (o && (strcmp(o, "sgd") == 0 || strcmp(o, "SGD") == 0 || strcmp(o, "1") == 0)) opt = Optimizer::SGD;
+  return new Server(opt);
+}
+
+static xf_table* make_table(Optimizer opt, int K, int device) {
+  xf_table_config cfg;
+  xf_table_config_default(&cfg);
+  cfg.device = device;
+  cfg.latent_dim = K;
+  cfg.optimizer = (opt == Optimizer::FTRL) ? XF_OPTIMIZER_FTRL : XF_OPTIMIZER_SGD;
+  cfg.alpha = alpha; cfg.beta = beta; cfg.lambda1 = lambda1; cfg.lambda2 = lambda2;
+  cfg.learning_rate = learning_rate;
+  cfg.seed = (uint64_t)env_int("XFLOW_SEED", 0);
+  cfg.capacity = (uint64_t)1 << env_int("XFLOW_TABLE_LOG2", 20);
+  xf_table* t = nullptr;
+  must(xf_table_create(&t, &cfg), "xf_table_create");
+  return t;
+}
+
+xf_table* Server::table_lr() {
+  if (!lr_) lr_ = make_table(opt_, 0, device_);
+  return lr_;
+}
+xf_table* Server::table_fm() {
+  if (!fm_) fm_ = make_table(opt_, latent_dim_ > 0 ? latent_dim_ : v_dim, device_);
+  return fm_;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workers
+// ------------------------------------------------------------------------------------------------
+WorkerBase::WorkerBase(const char* train_file, const char* test_file, int model)
+    : model_(model), train_file_path(train_file ? train_file : ""), test_file_path(test_file ? test_file : "") {
+  // the reference keeps the caller's pointers (lr_worker.h:81-82); we copy the strings
+  core_num = env_int("XFLOW_CORE_NUM", 1);
+  if (core_num < 1) core_num = 1;
+  block_size = env_int("XFLOW_BLOCK_MB", 2);
+  test_block_size = (model == XF_MODEL_LR) ? 4 : 2;
+  Server* s = Server::Get();
+  table_ = (model == XF_MODEL_LR) ? s->table_lr() : s->table_fm();
+  train_data_path[0] = test_data_path[0] = '\0';
+}
+
+WorkerBase::~WorkerBase() {
+  if (trainer_) xf_trainer_destroy(trainer_);
+}
+
+LRWorker::LRWorker(const char* train_file, const char* test_file) : WorkerBase(train_file, test_file, XF_MODEL_LR) {}
+FMWorker::FMWorker(const char* train_file, const char* test_file) : WorkerBase(train_file, test_file, XF_MODEL_FM) {}
+
+void WorkerBase::ensure_trainer(uint32_t rows, uint32_t nnz) {
+  if (trainer_ && rows <= trainer_rows_ && nnz <= trainer_nnz_) return;
+  if (trainer_) {
+    must(xf_trainer_sync(trainer_), "xf_trainer_sync");
+    xf_trainer_destroy(trainer_);
+    trainer_ = nullptr;
+  }
+  xf_trainer_config cfg;
+  cfg.model = model_;
+  cfg.max_rows = rows + rows / 4 + 16;
+  cfg.max_nnz = nnz + nnz / 4 + 16;
+  cfg.keep_loss = 0;
+  must(xf_trainer_create(&trainer_, table_, nullptr, &cfg), "xf_trainer_create");
+  trainer_rows_ = cfg.max_rows;
+  trainer_nnz_ = cfg.max_nnz;
+}
+
+// rows [start,end) of the current block, as one fused device step
+void WorkerBase::update(int start, int end) {
+  if (end <= start) return;
+  const uint32_t base = cur_row_ptr_[start];
+  const uint32_t rows = (uint32_t)(end - start);
+  const uint32_t nnz = cur_row_ptr_[end] - base;
+  const uint32_t* rp = cur_row_ptr_ + start;
+  if (base != 0) {
+    // slice offsets must start at 0 for the step's CSR view
+    slice_row_ptr_.resize(rows + 1);
+    for (uint32_t i = 0; i <= rows; ++i) slice_row_ptr_[i] = cur_row_ptr_[start + i] - base;
+    rp = slice_row_ptr_.data();
+  }
+  ensure_trainer(rows, nnz);
+  must(xf_trainer_step_host(trainer_, rp, cur_keys_ + base, cur_labels_ + start, rows, nnz, nullptr),
+       "xf_trainer_step_host");
+  rows_trained += rows;
+}
+
+void WorkerBase::batch_training() {
+  ensure_trainer(1024, 65536);
+  must(xf_trainer_init_push(trainer_), "xf_trainer_init_push");  // lr_worker.cc:180-182
+  for (int epoch = 0; epoch < epochs; ++epoch) {
+    xf_loader* loader = nullptr;
+    must(xf_loader_open(&loader, train_data_path, (uint64_t)block_size << 20), "xf_loader_open");  // :184
+    int block = 0;
+    while (true) {
+      // the loader alternates two output sets; before it overwrites one, the copies that read it
+      // must have drained
+      if (trainer_) must(xf_trainer_wait_uploads(trainer_), "xf_trainer_wait_uploads");
+      uint32_t rows = 0, nnz = 0;
+      must(xf_loader_next(loader, &rows, &nnz), "xf_loader_next");
+      if (rows == 0) break;  // :189
+      must(xf_loader_batch(loader, &cur_row_ptr_, &cur_keys_, &cur_labels_), "xf_loader_batch");
+      const int thread_size = (int)rows / core_num;  // :190 — remainder rows are dropped, as in the reference
+      for (int i = 0; i < core_num; ++i) update(i * thread_size, (i + 1) * thread_size);  // :192-196
+      ++block;
+    }
+    must(xf_trainer_sync(trainer_), "xf_trainer_sync");
+    xf_loader_close(loader);
+    if ((epoch + 1) % 30 == 0) std::cout << "epoch : " << epoch << std::endl;  // :202
+  }
+  cur_row_ptr_ = nullptr;
+  cur_keys_ = nullptr;
+  cur_labels_ = nullptr;
+}
+
+void WorkerBase::calculate_pctr(int start, int end) {
+  if (end <= start) return;
+  const uint32_t base = cur_row_ptr_[start];
+  const uint32_t rows = (uint32_t)(end - start);
+  const uint32_t nnz = cur_row_ptr_[end] - base;
+  const uint32_t* rp = cur_row_ptr_ + start;
+  if (base != 0) {
+    slice_row_ptr_.resize(rows + 1);
+    for (uint32_t i = 0; i <= rows; ++i) slice_row_ptr_[i] = cur_row_ptr_[start + i] - base;
+    rp = slice_row_ptr_.data();
+  }
+  ensure_trainer(rows, nnz);
+  std::vector<float> pctr(rows);
+  must(xf_trainer_predict_host(trainer_, rp, cur_keys_ + base, rows, nnz, pctr.data()), "xf_trainer_predict_host");
+  for (uint32_t i = 0; i < rows; ++i) {
+    auc_key ak;
+    ak.label = cur_labels_[start + i];
+    ak.pctr = pctr[i];
+    test_auc_vec.push_back(ak);
+    md << pctr[i] << "\t" << 1 - ak.label << "\t" << ak.label << std::endl;  // lr_worker.cc:67
+  }
+}
+
+void WorkerBase::predict(int rank_arg, int block) {
+  char buffer[1024];
+  snprintf(buffer, 1024, "%d_%d", rank_arg, block);
+  std::string filename = buffer;
+  md.open("pred_" + filename + ".txt");  // lr_worker.cc:77
+  if (!md.is_open()) std::cout << "open pred file failure!" << std::endl;
+  snprintf(test_data_path, 1024, "%s-%05d", test_file_path.c_str(), rank_arg);
+  xf_loader* loader = nullptr;
+  must(xf_loader_open(&loader, test_data_path, (uint64_t)test_block_size << 20), "xf_loader_open");
+  test_auc_vec.clear();
+  while (true) {
+    uint32_t rows = 0, nnz = 0;
+    must(xf_loader_next(loader, &rows, &nnz), "xf_loader_next");
+    if (rows == 0) break;
+    must(xf_loader_batch(loader, &cur_row_ptr_, &cur_keys_, &cur_labels_), "xf_loader_batch");
+    const int thread_size = (int)rows / core_num;
+    for (int i = 0; i < core_num; ++i) calculate_pctr(i * thread_size, (i + 1) * thread_size);
+  }
+  xf_loader_close(loader);
+  md.close();
+  cur_row_ptr_ = nullptr;
+  cur_keys_ = nullptr;
+  cur_labels_ = nullptr;
+
+  // Base::calculate_auc (base.h:84-110), same printout
+  std::vector<int32_t> labels(test_auc_vec.size());
+  std::vector<float> pctr(test_auc_vec.size());
+  for (size_t i = 0; i < test_auc_vec.size(); ++i) {
+    labels[i] = test_auc_vec[i].label;
+    pctr[i] = test_auc_vec[i].pctr;
+  }
+  double m[4] = {0, 0, 0, 0};
+  xf_auc_logloss(labels.data(), pctr.data(), labels.size(), m);
+  last_logloss = m[0];
+  last_auc = m[1];
+  std::cout << "logloss: " << (float)m[0] << "\t";
+  if (m[2] == 0 || m[3] == 0) {
+    std::cout << "tp_n = " << (int)m[2] << std::endl;
+  } else {
+    std::cout << "auc = " << (float)m[1] << "\ttp = " << (int)m[2] << " fp = " << (size_t)m[3] << std::endl;
+  }
+}
+
+void WorkerBase::train() {
+  rank = MyRank();
+  std::cout << "my rank is = " << rank << std::endl;
+  snprintf(train_data_path, 1024, "%s-%05d", train_file_path.c_str(), rank);
+  batch_training();
+  if (rank == 0) {
+    std::cout << model_name() << " AUC: " << std::endl;
+    predict(rank, 0);
+  }
+  std::cout << "train end......" << std::endl;
+}
+
+}  // namespace xflow
+
+// ------------------------------------------------------------------------------------------------
+// reference C API  (src/c_api/c_api.h:26-41, c_api.cc:10-20)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct XFlowHandle {  // the reference's `class XFlow { LRWorker* lr_worker_; }`
+  xflow::WorkerBase* worker = nullptr;
+};
+
+int xf_guard(const char* what, const std::function<void()>& fn) {
+  try {
+    fn();
+    return XF_OK;
+  } catch (const std::exception& e) {
+    xf_set_error("%s: %s", what, e.what());
+    return XF_ERR_STATE;
+  } catch (...) {
+    xf_set_error("%s: unknown exception", what);
+    return XF_ERR_STATE;
+  }
+}
+}  // namespace
+
+XF_DLL int XFCreateEx(void** h, const char* train_path, const char* test_path, int model, int optimizer,
+                      int latent_dim, int epochs) {
+  if (!h || !train_path || !test_path) { xf_set_error("null argument"); return XF_ERR_ARG; }
+  return xf_guard("XFCreate", [&]() {
+    if (latent_dim > 0) xflow::v_dim = latent_dim;
+    if (optimizer >= 0) {
+      // make sure a server with the requested optimizer exists before the worker attaches
+      bool need;
+      {
+        std::lock_guard<std::mutex> lk(xflow::g_mu);
+        need = (xflow::g_server == nullptr);
+      }
+      if (need) new xflow::Server(optimizer == XF_OPTIMIZER_SGD ? xflow::Optimizer::SGD : xflow::Optimizer::FTRL);
+    }
+    XFlowHandle* xf = new XFlowHandle;
+    if (model == XF_MODEL_FM) xf->worker = new xflow::FMWorker(train_path, test_path);
+    else xf->worker = new xflow::LRWorker(train_path, test_path);
+    if (epochs > 0) xf->worker->epochs = epochs;
+    *h = xf;
+  });
+}
+
+XF_DLL int XFCreate(void** h, const char* train_path, const char* test_path) {
+  const char* e = getenv("XFLOW_EPOCHS");
+  return XFCreateEx(h, train_path, test_path, XF_MODEL_LR, -1, 0, (e && *e) ? atoi(e) : 0);
+}
+
+XF_DLL int XFStartTrain(void** h) {
+  if (!h || !*h) { xf_set_error("null handle"); return XF_ERR_ARG; }
+  XFlowHandle* xf = reinterpret_cast<XFlowHandle*>(*h);
+  return xf_guard("XFStartTrain", [&]() { xf->worker->train(); });
+}
+
+XF_DLL int XFDestroy(void** h) {
+  if (!h || !*h) return XF_OK;
+  XFlowHandle* xf = reinterpret_cast<XFlowHandle*>(*h);
+  delete xf->worker;
+  delete xf;
+  *h = nullptr;
+  return XF_OK;
+}
