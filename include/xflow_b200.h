@@ -167,6 +167,22 @@ XF_DLL int xf_trainer_sync(xf_trainer* tr);
 /* block until every host->device batch copy issued so far has finished (the caller may then
  * overwrite host buffers it passed to xf_trainer_step_host with mean_abs_loss == NULL) */
 XF_DLL int xf_trainer_wait_uploads(xf_trainer* tr);
+/* Asynchronous variant of xf_trainer_step_host for pipelined callers: the batch arrays and
+ * `pinned_abs_loss_sum` (one float, receives sum |pctr - label| of this batch by an asynchronous
+ * device->host copy) must be page-locked host memory and stay untouched until xf_trainer_sync /
+ * xf_trainer_wait_uploads.  Never blocks on the device. */
+XF_DLL int xf_trainer_step_host_async(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys,
+                                      const uint8_t* labels, uint32_t rows, uint32_t nnz,
+                                      float* pinned_abs_loss_sum);
+/* Per-kernel device timing for roofline reporting.  on != 0: record CUDA events around the kernels
+ * of every following step (on the table's stream).  xf_trainer_profile syncs and returns, summed
+ * over the profiled steps since the last call: ms[0] = fused step kernel, ms[1] = optimizer kernel
+ * (+ batch bookkeeping), and the number of steps. */
+XF_DLL int xf_trainer_set_profile(xf_trainer* tr, int on);
+XF_DLL int xf_trainer_profile(xf_trainer* tr, double ms[2], uint64_t* steps);
+/* page-locked host memory for callers without a CUDA runtime of their own */
+XF_DLL int xf_host_alloc(void** out, uint64_t bytes);
+XF_DLL int xf_host_free(void* p);
 
 /* Base::calculate_auc (base.h:84-110), host: out[0]=logloss (base-2, not negated, float accumulator)
  * out[1]=auc (float `area`; NaN when single-class) out[2]=tp out[3]=fp */

@@ -72,6 +72,7 @@ def lib():
     L.xo_init_push.argtypes = [vp]
     L.xo_predict.argtypes = [vp, vp, vp, i64, vp]
     L.xo_auc_logloss.argtypes = [vp, vp, i64, vp]
+    L.xo_set_exact_sums.argtypes = [C.c_int]
     _lib = L
     return L
 
@@ -203,6 +204,17 @@ class Table:
         p = np.empty(B, np.float32)
         lib().xo_predict(self.h, _p(row_ptr), _p(keys), B, _p(p))
         return p
+
+
+class exact_sums:
+    """Context manager: accumulate the per-key gradient sums in double (analysis aid that measures the
+    float32 summation-order noise of the reference itself; NOT the reference's arithmetic)."""
+
+    def __enter__(self):
+        lib().xo_set_exact_sums(1)
+
+    def __exit__(self, *a):
+        lib().xo_set_exact_sums(0)
 
 
 def auc_logloss(labels, pctr):

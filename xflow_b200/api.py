@@ -70,6 +70,11 @@ SIGNATURES = {
     "xf_trainer_launches": (_i, [_vp, _vp]),
     "xf_trainer_sync": (_i, [_vp]),
     "xf_trainer_wait_uploads": (_i, [_vp]),
+    "xf_trainer_step_host_async": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "xf_trainer_set_profile": (_i, [_vp, _i]),
+    "xf_trainer_profile": (_i, [_vp, _vp, _vp]),
+    "xf_host_alloc": (_i, [_vp, _u64]),
+    "xf_host_free": (_i, [_vp]),
     "xf_auc_logloss": (_i, [_vp, _vp, _u64, _vp]),
     "xf_hash_bytes": (_u64, [C.c_char_p, _u64]),
     "xf_hash_decimal_ids": (_i, [_vp, _u64, _vp]),
@@ -325,6 +330,23 @@ class Trainer:
         _check(lib().xf_trainer_step_host(self.h, _p(row_ptr_addr), _p(keys_addr), _p(labels_addr), rows, nnz,
                                           C.byref(loss) if want_loss else None))
         return loss.value if want_loss else None
+
+    def step_host_async(self, row_ptr_addr, keys_addr, labels_addr, rows, nnz, out_addr=None):
+        """Pipelined step on page-locked buffers given by address; never blocks on the device."""
+        _check(lib().xf_trainer_step_host_async(self.h, _p(row_ptr_addr), _p(keys_addr), _p(labels_addr), rows, nnz,
+                                                _p(out_addr) if out_addr else None))
+
+    def wait_uploads(self):
+        _check(lib().xf_trainer_wait_uploads(self.h))
+
+    def set_profile(self, on):
+        _check(lib().xf_trainer_set_profile(self.h, 1 if on else 0))
+
+    def profile(self):
+        ms = (C.c_double * 2)()
+        steps = C.c_uint64()
+        _check(lib().xf_trainer_profile(self.h, ms, C.byref(steps)))
+        return dict(step_ms=ms[0], update_ms=ms[1], steps=steps.value)
 
     def step_device(self, d_row_ptr, d_keys, d_labels, rows, nnz):
         _check(lib().xf_trainer_step_device(self.h, _p(d_row_ptr), _p(d_keys), _p(d_labels), rows, nnz))

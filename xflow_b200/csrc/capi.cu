@@ -538,16 +538,30 @@ static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const 
   if (tr->mg) return xf_mg_step(tr, d_row_ptr, d_keys, d_labels, rows, nnz, mode, d_abs);
   XF_TRY(t->ensure_room(nnz));
   cudaStream_t st = t->stream;
+  const bool prof = tr->profile && mode == 0;
+  cudaEvent_t* pe = nullptr;
+  if (prof) {
+    if (tr->prof_used + 3 > tr->prof_events.size()) {
+      size_t old = tr->prof_events.size();
+      tr->prof_events.resize(old + 3 * 256);
+      for (size_t i = old; i < tr->prof_events.size(); ++i) XF_CUDA_TRY(cudaEventCreate(&tr->prof_events[i]));
+    }
+    pe = &tr->prof_events[tr->prof_used];
+    tr->prof_used += 3;
+    XF_CUDA_TRY(cudaEventRecord(pe[0], st));
+  }
   xf_launch_step(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
                  tr->d_touched_cnt, (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
                  mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
   ++tr->launches;
+  if (prof) XF_CUDA_TRY(cudaEventRecord(pe[1], st));
   if (mode == 0) {
     // Push + server-side optimizer: one FTRL/SGD step per touched key with g / rows
     xf_launch_update_touched(t->view, tr->touched.as<uint32_t>(), tr->d_touched_cnt, nnz, (double)rows, st);
     xf_launch_batch_end(tr->d_touched_cnt, tr->d_unique_total, st);
     tr->launches += 2;
   }
+  if (prof) XF_CUDA_TRY(cudaEventRecord(pe[2], st));
   XF_CUDA_TRY(cudaGetLastError());
   return XF_OK;
 }
@@ -704,5 +718,69 @@ XF_DLL int xf_trainer_sync(xf_trainer* tr) {
 XF_DLL int xf_trainer_wait_uploads(xf_trainer* tr) {
   if (!tr) return XF_ERR_ARG;
   XF_CUDA_TRY(cudaStreamSynchronize(tr->copy_stream));
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_step_host_async(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys,
+                                      const uint8_t* labels, uint32_t rows, uint32_t nnz,
+                                      float* pinned_abs_loss_sum) {
+  if (!tr || !row_ptr || (!keys && nnz) || !labels) return XF_ERR_ARG;
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  if (rows == 0) return XF_OK;
+  if (!xf_is_pinned(row_ptr) || !xf_is_pinned(keys) || !xf_is_pinned(labels) ||
+      (pinned_abs_loss_sum && !xf_is_pinned(pinned_abs_loss_sum))) {
+    xf_set_error("xf_trainer_step_host_async needs page-locked host buffers");
+    return XF_ERR_ARG;
+  }
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const int slot = (int)(tr->step_index & 1);
+  XfBatchBuf& b = tr->buf[slot];
+  ++tr->step_index;
+  XF_TRY(xf_upload_batch(tr, b, row_ptr, keys, labels, rows, nnz));
+  cudaStream_t st = tr->table->stream;
+  XF_CUDA_TRY(cudaMemsetAsync(tr->d_abs_loss + slot, 0, sizeof(float), st));
+  XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows,
+                             nnz, 0, tr->d_abs_loss + slot));
+  XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
+  if (pinned_abs_loss_sum)
+    XF_CUDA_TRY(cudaMemcpyAsync(pinned_abs_loss_sum, tr->d_abs_loss + slot, sizeof(float), cudaMemcpyDeviceToHost, st));
+  ++tr->n_steps;
+  tr->n_rows += rows;
+  tr->n_nnz += nnz;
+  tr->last_rows = rows;
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_set_profile(xf_trainer* tr, int on) {
+  if (!tr) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
+  tr->profile = on != 0;
+  tr->prof_used = 0;
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_profile(xf_trainer* tr, double ms[2], uint64_t* steps) {
+  if (!tr || !ms) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
+  ms[0] = ms[1] = 0.0;
+  for (size_t i = 0; i + 3 <= tr->prof_used; i += 3) {
+    float a = 0.f, b = 0.f;
+    XF_CUDA_TRY(cudaEventElapsedTime(&a, tr->prof_events[i], tr->prof_events[i + 1]));
+    XF_CUDA_TRY(cudaEventElapsedTime(&b, tr->prof_events[i + 1], tr->prof_events[i + 2]));
+    ms[0] += a;
+    ms[1] += b;
+  }
+  if (steps) *steps = tr->prof_used / 3;
+  tr->prof_used = 0;
+  return XF_OK;
+}
+
+XF_DLL int xf_host_alloc(void** out, uint64_t bytes) {
+  if (!out) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return XF_OK;
+}
+XF_DLL int xf_host_free(void* p) {
+  if (p) XF_CUDA_TRY(cudaFreeHost(p));
   return XF_OK;
 }

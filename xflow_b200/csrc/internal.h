@@ -88,6 +88,10 @@ struct xf_trainer {
   uint32_t last_rows = 0;
   uint64_t launches = 0;
   void* mg = nullptr;                   // multi-GPU exchange state (comm.cu)
+  // optional per-kernel timing (xf_trainer_set_profile): events around the kernels of each step
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;  // XF_PROF_MARKS per step
+  size_t prof_used = 0;
 };
 
 // multi-GPU pieces implemented in comm.cu

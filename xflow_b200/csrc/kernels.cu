@@ -38,7 +38,7 @@ __global__ void xf_k_fill(uint8_t* base, uint64_t cap, uint32_t stride) {
     uint32_t q = (uint32_t)(c % chunks_per_row);
     uint4 v = make_uint4(0, 0, 0, 0);
     if (q == 0) { v.x = 0xFFFFFFFFu; v.y = 0xFFFFFFFFu; }
-    if (q == 1) { v.w = XF_NEG_ZERO_BITS; }
+    if (q == 1) { v.w = XF_NEG_ZERO_BITS; }  // high word of the f64 accumulator g = -0.0
     *reinterpret_cast<uint4*>(base + r * stride + (uint64_t)q * 16) = v;
   }
 }
@@ -190,12 +190,12 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
       bool first = false;
       if (s >= 0) {
         uint8_t* rowp = xf_row(t, (uint64_t)s);
-        const float old = atomicAdd(xf_row_g(rowp), gw_c);
-        first = (__float_as_uint(old) == XF_NEG_ZERO_BITS);
+        const double old = atomicAdd(xf_row_g(rowp), (double)gw_c);
+        first = ((unsigned long long)__double_as_longlong(old) == XF_NEG_ZERO_BITS64);
         if (FM) {
           const float* vp = xf_row_v(rowp);
           float* gvp = xf_row_gv(rowp, K);
-          const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + 8));
+          const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
           const bool ready = (flags & XF_FLAG_V_READY) != 0;
           const uint64_t key = ready ? 0ull : __ldg(keys + j);
           for (int k = 0; k < K; k += VEC) {
@@ -267,20 +267,25 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, const unsigned in
       const uint32_t s = slots[i];
       if (s != 0xFFFFFFFFu) {
         rowp = xf_row(t, s);
-        uint4 a = __ldcg(reinterpret_cast<const uint4*>(rowp));
-        key = (uint64_t)a.x | ((uint64_t)a.y << 32);
-        flags = a.z;
+        key = __ldcg(reinterpret_cast<const unsigned long long*>(rowp));
+        flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
       }
     }
     __syncwarp(group_mask);  // every lane of the group has read `flags` before lane 0 rewrites it
     if (rowp == nullptr) continue;
 
     if (q == 0 && (part & 1)) {
-      float4 b = __ldcg(reinterpret_cast<const float4*>(rowp + 16));
-      float g = SLOTG ? xf_div_rows(b.w, rows) : gw[i];
-      xf_opt_coord(t, g, b.x, b.y, b.z);
-      if (SLOTG) b.w = -0.0f;
-      *reinterpret_cast<float4*>(rowp + 16) = b;
+      XfHead h = xf_load_head(rowp);
+      // the accumulated sum is rounded to float once (push_gradient is a float vector), then / rows
+      float g = SLOTG ? xf_div_rows((float)h.g, rows) : gw[i];
+      xf_opt_coord(t, g, h.w, h.n, h.z);
+      *reinterpret_cast<float2*>(rowp + 8) = make_float2(h.w, h.n);
+      if (SLOTG) {
+        // z, flags (unchanged here; V_READY is set below), g = -0.0 "untouched" marker
+        *reinterpret_cast<uint4*>(rowp + 16) = make_uint4(__float_as_uint(h.z), flags, 0u, XF_NEG_ZERO_BITS);
+      } else {
+        *reinterpret_cast<float*>(rowp + 16) = h.z;
+      }
     }
     if (K > 0 && (part & 2)) {
       const bool ready = (flags & XF_FLAG_V_READY) != 0;
@@ -328,7 +333,7 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, const unsigned in
           xf_stv<VEC>(gvp + k, zero);
         }
       }
-      if (q == 0 && !ready) *reinterpret_cast<uint32_t*>(rowp + 8) = flags | XF_FLAG_V_READY;
+      if (q == 0 && !ready) *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = flags | XF_FLAG_V_READY;
     }
   }
 }
@@ -371,7 +376,7 @@ __global__ void xf_k_gather_v(XfTableView t, const uint32_t* __restrict__ slots,
     float v = 0.f;
     if (s != 0xFFFFFFFFu) {
       const uint8_t* rowp = xf_row(t, s);
-      const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + 8));
+      const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
       v = (flags & XF_FLAG_V_READY) ? __ldcg(reinterpret_cast<const float*>(rowp + 32) + k)
                                     : xf_v_init(t, keys[i], (uint32_t)k);
     }
@@ -395,10 +400,11 @@ __global__ void xf_k_import(XfTableView t, const uint32_t* __restrict__ slots, u
     uint8_t* rowp = xf_row(t, s);
     if (c == 0) {
       if (w) {
-        float4 b = make_float4(w[i], nw ? nw[i] : 0.f, zw ? zw[i] : 0.f, -0.0f);
-        *reinterpret_cast<float4*>(rowp + 16) = b;
+        *reinterpret_cast<float2*>(rowp + 8) = make_float2(w[i], nw ? nw[i] : 0.f);
+        *reinterpret_cast<float*>(rowp + 16) = zw ? zw[i] : 0.f;
+        *reinterpret_cast<unsigned long long*>(rowp + 24) = XF_NEG_ZERO_BITS64;
       }
-      if (v && K > 0) *reinterpret_cast<uint32_t*>(rowp + 8) = XF_FLAG_V_READY;
+      if (v && K > 0) *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = XF_FLAG_V_READY;
     } else if (v) {
       const int k = c - 1;
       xf_row_v(rowp)[k] = v[i * K + k];
@@ -426,16 +432,18 @@ __global__ void xf_k_export(XfTableView t, const uint32_t* __restrict__ slots, c
     const bool have = s != 0xFFFFFFFFu;
     const uint8_t* rowp = have ? xf_row(t, s) : nullptr;
     if (c == 0) {
-      float4 b = have ? __ldcg(reinterpret_cast<const float4*>(rowp + 16)) : make_float4(0, 0, 0, 0);
+      XfHead h;
+      h.w = h.n = h.z = 0.f;
+      if (have) h = xf_load_head(rowp);
       if (present) present[i] = have ? 1 : 0;
-      if (w) w[i] = b.x;
-      if (nw) nw[i] = b.y;
-      if (zw) zw[i] = b.z;
+      if (w) w[i] = h.w;
+      if (nw) nw[i] = h.n;
+      if (zw) zw[i] = h.z;
     } else if (v) {
       const int k = c - 1;
       float vv = 0.f, nn = 0.f, zz = 0.f;
       if (have) {
-        const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + 8));
+        const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
         if (flags & XF_FLAG_V_READY) {
           vv = __ldcg(reinterpret_cast<const float*>(rowp + 32) + k);
           if (t.opt == XF_OPT_FTRL) {
@@ -467,7 +475,7 @@ __global__ void xf_k_rehash(XfTableView src, XfTableView dst) {
     int64_t s = xf_probe<true>(dst, key, &h);
     if (s < 0) continue;
     uint8_t* drow = xf_row(dst, (uint64_t)s);
-    // the key word is already in place (CAS); copy flags and everything after
+    // the key word is already in place (CAS); copy w, n and everything after
     *reinterpret_cast<uint2*>(drow + 8) = make_uint2(a.z, a.w);
     for (uint32_t c = 1; c < chunks; ++c)
       *reinterpret_cast<uint4*>(drow + 16 * c) = *reinterpret_cast<const uint4*>(srow + 16 * c);

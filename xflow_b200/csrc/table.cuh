@@ -7,12 +7,14 @@
 //
 //   byte  0  u64  key            (EMPTY = 2^64-1; never a legal key in the reference either:
 //                                 it lies outside every server range, postoffice.cc:134-143)
-//   byte  8  u32  flags          bit0 = latent block materialised (V_READY)
-//   byte 12  u32  reserved
-//   byte 16  f32  w              app-0 weight                         (FTRLEntry_w::w / SGDEntry_w::w)
-//   byte 20  f32  n              FTRL accumulator of w (unused by SGD)
-//   byte 24  f32  z              FTRL accumulator of w (unused by SGD)
-//   byte 28  f32  g              per-batch gradient accumulator of w; -0.0f == "untouched this batch"
+//   byte  8  f32  w              app-0 weight                         (FTRLEntry_w::w / SGDEntry_w::w)
+//   byte 12  f32  n              FTRL accumulator of w (unused by SGD)
+//   byte 16  f32  z              FTRL accumulator of w (unused by SGD)
+//   byte 20  u32  flags          bit0 = latent block materialised (V_READY)
+//   byte 24  f64  g              per-batch gradient accumulator of w; -0.0 == "untouched this batch".
+//                                Double, so that the sum over a key's occurrences is exact to float
+//                                precision whatever order the L2 atomics land in (deterministic, and
+//                                more accurate than the reference's own sequential float sum).
 //   ---- 32 B = one DRAM sector: an LR pull, gradient accumulate or update touches exactly one ----
 //   byte 32            f32 v[K]    app-1 latent row
 //   byte 32 +   4K     f32 gv[K]   per-batch gradient accumulator of v
@@ -32,6 +34,7 @@
 #define XF_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define XF_FLAG_V_READY 1u
 #define XF_NEG_ZERO_BITS 0x80000000u
+#define XF_NEG_ZERO_BITS64 0x8000000000000000ull
 #define XF_MAX_PROBE 8192
 
 enum { XF_OPT_FTRL = 0, XF_OPT_SGD = 1 };
@@ -94,7 +97,8 @@ __device__ __forceinline__ float xf_v_init(const XfTableView& t, uint64_t key, u
 __device__ __forceinline__ uint8_t* xf_row(const XfTableView& t, uint64_t slot) {
   return t.base + slot * (uint64_t)t.stride;
 }
-__device__ __forceinline__ float* xf_row_g(uint8_t* row) { return reinterpret_cast<float*>(row + 28); }
+__device__ __forceinline__ double* xf_row_g(uint8_t* row) { return reinterpret_cast<double*>(row + 24); }
+#define XF_OFF_FLAGS 20
 __device__ __forceinline__ float* xf_row_v(uint8_t* row) { return reinterpret_cast<float*>(row + 32); }
 __device__ __forceinline__ float* xf_row_gv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + 32) + K; }
 __device__ __forceinline__ float* xf_row_nv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + 32) + 2 * K; }
@@ -103,17 +107,21 @@ __device__ __forceinline__ float* xf_row_zv(uint8_t* row, int K) { return reinte
 struct XfHead {
   uint64_t key;
   uint32_t flags;
-  float w, n, z, g;
+  float w, n, z;
+  double g;
 };
 
 __device__ __forceinline__ XfHead xf_load_head(const uint8_t* row) {
   // one 32-byte sector, two 16-byte L2 loads (L1 is useless for random rows)
   uint4 a = __ldcg(reinterpret_cast<const uint4*>(row));
-  float4 b = __ldcg(reinterpret_cast<const float4*>(row + 16));
+  uint4 b = __ldcg(reinterpret_cast<const uint4*>(row + 16));
   XfHead h;
   h.key = (uint64_t)a.x | ((uint64_t)a.y << 32);
-  h.flags = a.z;
-  h.w = b.x; h.n = b.y; h.z = b.z; h.g = b.w;
+  h.w = __uint_as_float(a.z);
+  h.n = __uint_as_float(a.w);
+  h.z = __uint_as_float(b.x);
+  h.flags = b.y;
+  h.g = __longlong_as_double((long long)((uint64_t)b.z | ((uint64_t)b.w << 32)));
   return h;
 }
 
@@ -140,7 +148,7 @@ __device__ __forceinline__ int64_t xf_probe(const XfTableView& t, uint64_t key, 
         unsigned m = __activemask();
         int leader = __ffs(m) - 1;
         if ((int)(threadIdx.x & 31) == leader) atomicAdd(t.size, (unsigned long long)__popc(m));
-        h.key = key; h.flags = 0; h.w = 0.f; h.n = 0.f; h.z = 0.f; h.g = -0.0f;
+        h.key = key; h.flags = 0; h.w = 0.f; h.n = 0.f; h.z = 0.f; h.g = -0.0;
         *head = h;
         return (int64_t)s;
       }
