@@ -154,6 +154,10 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
     return XF_ERR_ARG;
   }
   XF_CUDA_TRY(cudaSetDevice(cfg->device));
+  // The table is read and written one random 32-byte sector at a time.  The default L2 fetch
+  // granularity (64 B) doubles the DRAM traffic of every miss; ask for sector-sized fetches.
+  // (A hint: the driver may ignore it; measured with ncu dram__bytes_read.)
+  if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32) != cudaSuccess) cudaGetLastError();
   xf_table* t = new xf_table;
   t->cfg = *cfg;
   memset(&t->view, 0, sizeof(t->view));
@@ -183,6 +187,7 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
 
 XF_DLL int xf_table_destroy(xf_table* t) {
   if (!t) return XF_OK;
+  if (--t->refs > 0) return XF_OK;  // still used by a trainer; freed when the last user lets go
   cudaSetDevice(t->cfg.device);
   cudaStreamSynchronize(t->stream);
   if (t->view.base) cudaFree(t->view.base);
@@ -497,6 +502,7 @@ XF_DLL int xf_trainer_create(xf_trainer** out, xf_table* table, xf_comm* comm, c
     int r = xf_mg_create(tr);
     if (r != XF_OK) { delete tr; return r; }
   }
+  ++table->refs;
   *out = tr;
   return XF_OK;
 }
@@ -517,8 +523,10 @@ XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
   cudaFree(tr->d_touched_cnt); cudaFree(tr->d_unique_total); cudaFree(tr->d_abs_loss);
   cudaFreeHost(tr->h_abs_loss);
   cudaStreamDestroy(tr->copy_stream);
+  for (cudaEvent_t e : tr->prof_events) cudaEventDestroy(e);
+  xf_table* table = tr->table;
   delete tr;
-  return XF_OK;
+  return xf_table_destroy(table);  // drop the trainer's reference
 }
 
 static int xf_check_batch(xf_trainer* tr, uint32_t rows, uint32_t nnz) {
@@ -551,15 +559,14 @@ static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const 
     XF_CUDA_TRY(cudaEventRecord(pe[0], st));
   }
   xf_launch_step(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
-                 tr->d_touched_cnt, (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
+                 (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
                  mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
   ++tr->launches;
   if (prof) XF_CUDA_TRY(cudaEventRecord(pe[1], st));
   if (mode == 0) {
     // Push + server-side optimizer: one FTRL/SGD step per touched key with g / rows
-    xf_launch_update_touched(t->view, tr->touched.as<uint32_t>(), tr->d_touched_cnt, nnz, (double)rows, st);
-    xf_launch_batch_end(tr->d_touched_cnt, tr->d_unique_total, st);
-    tr->launches += 2;
+    xf_launch_update_touched(t->view, tr->touched.as<uint32_t>(), nnz, (double)rows, tr->d_unique_total, st);
+    ++tr->launches;
   }
   if (prof) XF_CUDA_TRY(cudaEventRecord(pe[2], st));
   XF_CUDA_TRY(cudaGetLastError());

@@ -55,6 +55,7 @@ struct xf_table {
   int* d_error = nullptr;
   uint64_t size_bound = 0;   // host-side upper bound on the number of live keys
   uint64_t launches = 0;
+  int refs = 1;              // the creator + every trainer bound to the table (destroy order is free)
   // scratch for the host-pointer API
   XfDevBuf s_keys, s_slots, s_w, s_v, s_nw, s_zw, s_nv, s_zv, s_present;
 

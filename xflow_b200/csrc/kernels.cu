@@ -78,164 +78,6 @@ __device__ __forceinline__ void xf_redv(float* p, const float (&o)[VEC]) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// fused worker step
-// -------------------------------------------------------------------------------------------------
-// One warp per row, lane per token.  Phase A: probe each token's key (inserting missing keys, as
-// the Pull would), read w from the row's first sector and, for FM, reduce the latent row to
-// (sum_k v, sum_k v^2).  Warp-segmented sums give wx (and S, Q), one lane-uniform sigmoid gives the
-// residual.  Phase B: every token adds its contribution to its key's accumulators with L2 atomics on
-// the sector it has just loaded; the lane that finds the untouched marker (-0.0f) in `g` appends the
-// slot to the batch's touched list, which the optimizer kernel consumes.
-//   mode: 0 = train, 1 = predict (no phase B; Pull still inserts, lr_worker.cc:47)
-#define XF_TOK_CACHE 4  // tokens per lane whose slot index is kept in registers (rows <= 128 tokens)
-
-template <bool FM, int VEC>
-__global__ void __launch_bounds__(256)
-xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* __restrict__ keys,
-          const uint8_t* __restrict__ labels, int B, int mode, uint32_t* __restrict__ touched,
-          unsigned int* __restrict__ touched_cnt, float* __restrict__ loss_out, float* __restrict__ pctr_out,
-          float* __restrict__ abs_loss_sum) {
-  __shared__ float s_abs[8];
-  float abs_acc = 0.f;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * warps_per_block;
-  const int K = t.K;
-
-  for (int row = gwarp; row < B; row += nwarps) {
-    const uint32_t beg = __ldg(row_ptr + row);
-    const uint32_t end = __ldg(row_ptr + row + 1);
-    const int iters = (int)((end - beg + 31u) >> 5);
-
-    float wsum = 0.f, ssum = 0.f, qsum = 0.f;
-    int64_t slot_c[XF_TOK_CACHE];
-#pragma unroll
-    for (int c = 0; c < XF_TOK_CACHE; ++c) slot_c[c] = -1;
-
-    // ---------------- phase A
-    for (int it = 0; it < iters; ++it) {
-      const uint32_t j = beg + (uint32_t)it * 32u + (uint32_t)lane;
-      int64_t s = -1;
-      if (j < end) {
-        const uint64_t key = __ldg(keys + j);
-        XfHead h;
-        s = xf_probe<true>(t, key, &h);
-        if (s >= 0) {
-          wsum += h.w;
-          if (FM) {
-            const uint8_t* rowp = xf_row(t, (uint64_t)s);
-            const float* vp = reinterpret_cast<const float*>(rowp + 32);
-            float st = 0.f, qt = 0.f;
-            if (h.flags & XF_FLAG_V_READY) {
-              for (int k = 0; k < K; k += VEC) {
-                float v[VEC];
-                xf_ldv<VEC>(vp + k, v);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) { st += v[e]; qt = __fadd_rn(qt, __fmul_rn(v[e], v[e])); }
-              }
-            } else {
-              for (int k = 0; k < K; ++k) {
-                float v = xf_v_init(t, key, (uint32_t)k);
-                st += v;
-                qt = __fadd_rn(qt, __fmul_rn(v, v));
-              }
-            }
-            ssum += st;
-            qsum += qt;
-          }
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < XF_TOK_CACHE; ++c)
-        if (it == c) slot_c[c] = s;
-    }
-
-    // ---------------- per-row reduction, sigmoid, residual
-    const float wx = xf_warp_sum(wsum);
-    float S = 0.f, arg = wx;
-    if (FM) {
-      S = xf_warp_sum(ssum);
-      const float Q = xf_warp_sum(qsum);
-      const float v_y = __fsub_rn(__fmul_rn(S, S), Q);  // fm_worker.cc:193-196
-      arg = __fadd_rn(wx, v_y);
-    }
-    const float pctr = xf_sigmoid(arg);
-    if (mode == 1) {
-      if (lane == 0 && pctr_out) pctr_out[row] = pctr;
-      continue;
-    }
-    const float loss = __fsub_rn(pctr, (float)labels[row]);  // lr_worker.cc:141 ; fm_worker.cc:200
-    if (lane == 0 && loss_out) loss_out[row] = loss;
-    abs_acc += fabsf(loss);
-
-    // ---------------- phase B
-    float gw_c = loss;
-    if (FM) {
-      // fm_worker.cc:140 accumulates the w-gradient inside the k loop: K sequential float adds
-      gw_c = 0.f;
-      for (int k = 0; k < K; ++k) gw_c += loss;
-    }
-    for (int it = 0; it < iters; ++it) {
-      const uint32_t j = beg + (uint32_t)it * 32u + (uint32_t)lane;
-      int64_t s = -1;
-      if (it < XF_TOK_CACHE) {
-#pragma unroll
-        for (int c = 0; c < XF_TOK_CACHE; ++c)
-          if (it == c) s = slot_c[c];
-      } else if (j < end) {
-        XfHead h;
-        s = xf_probe<false>(t, __ldg(keys + j), &h);
-      }
-      bool first = false;
-      if (s >= 0) {
-        uint8_t* rowp = xf_row(t, (uint64_t)s);
-        const double old = atomicAdd(xf_row_g(rowp), (double)gw_c);
-        first = ((unsigned long long)__double_as_longlong(old) == XF_NEG_ZERO_BITS64);
-        if (FM) {
-          const float* vp = xf_row_v(rowp);
-          float* gvp = xf_row_gv(rowp, K);
-          const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
-          const bool ready = (flags & XF_FLAG_V_READY) != 0;
-          const uint64_t key = ready ? 0ull : __ldg(keys + j);
-          for (int k = 0; k < K; k += VEC) {
-            float v[VEC], gc[VEC];
-            if (ready) {
-              xf_ldv<VEC>(vp + k, v);
-            } else {
-#pragma unroll
-              for (int e = 0; e < VEC; ++e) v[e] = xf_v_init(t, key, (uint32_t)(k + e));
-            }
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) gc[e] = __fmul_rn(loss, __fsub_rn(S, v[e]));  // fm_worker.cc:141-142
-            xf_redv<VEC>(gvp + k, gc);
-          }
-        }
-      }
-      // warp-aggregated append of first-touched slots
-      const unsigned m = __ballot_sync(0xffffffffu, first);
-      if (m) {
-        unsigned base = 0;
-        const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(touched_cnt, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (first) touched[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)s;
-      }
-    }
-  }
-  // monitoring scalar: sum over rows of |pctr - label| (one atomic per block)
-  if (abs_loss_sum != nullptr && mode == 0) {
-    if (lane == 0) s_abs[threadIdx.x >> 5] = abs_acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_abs[w];
-      atomicAdd(abs_loss_sum, tot);
-    }
-  }
-}
-
-// -------------------------------------------------------------------------------------------------
 // optimizer step over a list of rows
 // -------------------------------------------------------------------------------------------------
 // TPS (power of two <= 32) consecutive lanes own one row: lane q handles latent coordinates
@@ -245,10 +87,13 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
 //   SLOTG = false: gradients come from gw[i] / gv[i*K+k] (Push).  part bit0: apply w, bit1: apply v.
 template <int VEC, bool SLOTG>
 __global__ void __launch_bounds__(256)
-xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, const unsigned int* __restrict__ n_ptr,
-            uint64_t n_fixed, int tps, double rows, const float* __restrict__ gw,
-            const float* __restrict__ gv, int part) {
-  const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_fixed;
+xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int tps, double rows,
+            const float* __restrict__ gw, const float* __restrict__ gv, int part,
+            unsigned long long* __restrict__ live_total) {
+  __shared__ unsigned int s_live;
+  if (threadIdx.x == 0) s_live = 0;
+  __syncthreads();
+  unsigned int live_acc = 0;
   const int K = t.K;
   const uint64_t gthread = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
@@ -261,31 +106,33 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, const unsigned in
     const uint64_t i = x / (uint64_t)tps;
     const bool live = i < n;
     uint8_t* rowp = nullptr;
-    uint32_t flags = 0;
-    uint64_t key = 0;
     if (live) {
       const uint32_t s = slots[i];
-      if (s != 0xFFFFFFFFu) {
-        rowp = xf_row(t, s);
-        key = __ldcg(reinterpret_cast<const unsigned long long*>(rowp));
-        flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
-      }
+      if (s != 0xFFFFFFFFu) rowp = xf_row(t, s);
     }
-    __syncwarp(group_mask);  // every lane of the group has read `flags` before lane 0 rewrites it
+    // the group leader reads the head sector once (one 256-bit load) and shares key / flags
+    XfHead h;
+    h.key = 0; h.flags = 0; h.w = h.n = h.z = 0.f; h.g = 0.0;
+    if (q == 0 && rowp != nullptr) h = xf_load_head(rowp);
+    const int leader = (int)(lane & ~(unsigned)(tps - 1));
+    const uint64_t key = __shfl_sync(group_mask, (unsigned long long)h.key, leader);
+    const uint32_t flags = __shfl_sync(group_mask, h.flags, leader);
+    if (live_total != nullptr) {
+      // rows actually updated (= unique keys of the batch in the fused step): count per warp
+      const unsigned lm = __ballot_sync(0xffffffffu, q == 0 && rowp != nullptr);
+      if (lane == 0) live_acc += __popc(lm);
+    }
     if (rowp == nullptr) continue;
 
-    if (q == 0 && (part & 1)) {
-      XfHead h = xf_load_head(rowp);
-      // the accumulated sum is rounded to float once (push_gradient is a float vector), then / rows
-      float g = SLOTG ? xf_div_rows((float)h.g, rows) : gw[i];
-      xf_opt_coord(t, g, h.w, h.n, h.z);
-      *reinterpret_cast<float2*>(rowp + 8) = make_float2(h.w, h.n);
-      if (SLOTG) {
-        // z, flags (unchanged here; V_READY is set below), g = -0.0 "untouched" marker
-        *reinterpret_cast<uint4*>(rowp + 16) = make_uint4(__float_as_uint(h.z), flags, 0u, XF_NEG_ZERO_BITS);
-      } else {
-        *reinterpret_cast<float*>(rowp + 16) = h.z;
+    if (q == 0) {
+      if (part & 1) {
+        // the accumulated sum is rounded to float once (push_gradient is a float vector), then / rows
+        const float g = SLOTG ? xf_div_rows((float)h.g, rows) : gw[i];
+        xf_opt_coord(t, g, h.w, h.n, h.z);
       }
+      if (SLOTG) h.g = -0.0;  // "untouched" marker for the next batch
+      if (K > 0 && (part & 2)) h.flags |= XF_FLAG_V_READY;
+      xf_store_head(rowp, h);  // one full-sector store
     }
     if (K > 0 && (part & 2)) {
       const bool ready = (flags & XF_FLAG_V_READY) != 0;
@@ -333,16 +180,12 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, const unsigned in
           xf_stv<VEC>(gvp + k, zero);
         }
       }
-      if (q == 0 && !ready) *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = flags | XF_FLAG_V_READY;
     }
   }
-}
-
-// bookkeeping between batches: fold the touched count into the running total, clear the counter
-__global__ void xf_k_batch_end(unsigned int* touched_cnt, unsigned long long* unique_total) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    *unique_total += (unsigned long long)*touched_cnt;
-    *touched_cnt = 0;
+  if (live_total != nullptr) {
+    if (lane == 0 && live_acc) atomicAdd(&s_live, live_acc);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_live) atomicAdd(live_total, (unsigned long long)s_live);
   }
 }
 
@@ -498,7 +341,7 @@ __global__ void xf_k_list_keys(XfTableView t, uint64_t* keys_out, unsigned long 
 // host-side launchers (plain C++ signatures, see kernels.h)
 // -------------------------------------------------------------------------------------------------
 static int g_sm_count = 0;
-static int xf_sms() {
+int xf_sms() {
   if (g_sm_count == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -507,7 +350,7 @@ static int xf_sms() {
   }
   return g_sm_count;
 }
-static inline int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm) {
+int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm) {
   uint64_t want = (work_items + block - 1) / block;
   uint64_t cap = (uint64_t)xf_sms() * blocks_per_sm;
   if (want < 1) want = 1;
@@ -529,52 +372,30 @@ void xf_launch_fill(const XfTableView& t, cudaStream_t st) {
   xf_k_fill<<<xf_grid_for(total, 256, 16), 256, 0, st>>>(t.base, cap, t.stride);
 }
 
-void xf_launch_step(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* labels,
-                    int B, int mode, uint32_t* touched, unsigned int* touched_cnt, float* loss_out,
-                    float* pctr_out, float* abs_loss_sum, cudaStream_t st) {
-  if (B <= 0) return;
-  const int block = 256;
-  const int grid = xf_grid_for((uint64_t)B * 32, block, 8);
-  if (t.K == 0) {
-    xf_k_step<false, 1><<<grid, block, 0, st>>>(t, row_ptr, keys, labels, B, mode, touched, touched_cnt,
-                                                  loss_out, pctr_out, abs_loss_sum);
-  } else {
-    switch (xf_vec_for(t.K)) {
-      case 4: xf_k_step<true, 4><<<grid, block, 0, st>>>(t, row_ptr, keys, labels, B, mode, touched, touched_cnt, loss_out, pctr_out, abs_loss_sum); break;
-      case 2: xf_k_step<true, 2><<<grid, block, 0, st>>>(t, row_ptr, keys, labels, B, mode, touched, touched_cnt, loss_out, pctr_out, abs_loss_sum); break;
-      default: xf_k_step<true, 1><<<grid, block, 0, st>>>(t, row_ptr, keys, labels, B, mode, touched, touched_cnt, loss_out, pctr_out, abs_loss_sum); break;
-    }
-  }
-}
-
 template <bool SLOTG>
-static void xf_launch_update_t(const XfTableView& t, const uint32_t* slots, const unsigned int* n_ptr,
-                               uint64_t n_fixed, uint64_t n_max, double rows, const float* gw, const float* gv,
-                               int part, cudaStream_t st) {
+static void xf_launch_update_t(const XfTableView& t, const uint32_t* slots, uint64_t n, double rows,
+                               const float* gw, const float* gv, int part, unsigned long long* live_total,
+                               cudaStream_t st) {
   const int tps = xf_tps_for(t.K);
-  const int grid = xf_grid_for(n_max * (uint64_t)tps, 256, 8);
+  const int grid = xf_grid_for(n * (uint64_t)tps, 256, 8);
   switch (xf_vec_for(t.K)) {
-    case 4: xf_k_update<4, SLOTG><<<grid, 256, 0, st>>>(t, slots, n_ptr, n_fixed, tps, rows, gw, gv, part); break;
-    case 2: xf_k_update<2, SLOTG><<<grid, 256, 0, st>>>(t, slots, n_ptr, n_fixed, tps, rows, gw, gv, part); break;
-    default: xf_k_update<1, SLOTG><<<grid, 256, 0, st>>>(t, slots, n_ptr, n_fixed, tps, rows, gw, gv, part); break;
+    case 4: xf_k_update<4, SLOTG><<<grid, 256, 0, st>>>(t, slots, n, tps, rows, gw, gv, part, live_total); break;
+    case 2: xf_k_update<2, SLOTG><<<grid, 256, 0, st>>>(t, slots, n, tps, rows, gw, gv, part, live_total); break;
+    default: xf_k_update<1, SLOTG><<<grid, 256, 0, st>>>(t, slots, n, tps, rows, gw, gv, part, live_total); break;
   }
 }
 
-void xf_launch_update_touched(const XfTableView& t, const uint32_t* touched, const unsigned int* touched_cnt,
-                              uint64_t n_max, double rows, cudaStream_t st) {
-  if (n_max == 0) return;
-  xf_launch_update_t<true>(t, touched, touched_cnt, 0, n_max, rows, nullptr, nullptr, 3, st);
+void xf_launch_update_touched(const XfTableView& t, const uint32_t* touched, uint64_t nnz, double rows,
+                              unsigned long long* unique_total, cudaStream_t st) {
+  if (nnz == 0) return;
+  xf_launch_update_t<true>(t, touched, nnz, rows, nullptr, nullptr, 3, unique_total, st);
 }
 
 void xf_launch_update_pushed(const XfTableView& t, const uint32_t* slots, uint64_t n, const float* gw,
                              const float* gv, cudaStream_t st) {
   if (n == 0) return;
   int part = (gw ? 1 : 0) | (gv ? 2 : 0);
-  xf_launch_update_t<false>(t, slots, nullptr, n, n, 1.0, gw, gv, part, st);
-}
-
-void xf_launch_batch_end(unsigned int* touched_cnt, unsigned long long* unique_total, cudaStream_t st) {
-  xf_k_batch_end<<<1, 32, 0, st>>>(touched_cnt, unique_total);
+  xf_launch_update_t<false>(t, slots, n, 1.0, gw, gv, part, nullptr, st);
 }
 
 void xf_launch_probe(const XfTableView& t, const uint64_t* keys, uint64_t n, bool insert, uint32_t* slots,

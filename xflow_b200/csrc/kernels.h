@@ -10,13 +10,13 @@ int xf_tps_for(int K);
 
 void xf_launch_fill(const XfTableView& t, cudaStream_t st);
 void xf_launch_step(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* labels,
-                    int B, int mode, uint32_t* touched, unsigned int* touched_cnt, float* loss_out,
-                    float* pctr_out, float* abs_loss_sum, cudaStream_t st);
-void xf_launch_update_touched(const XfTableView& t, const uint32_t* touched, const unsigned int* touched_cnt,
-                              uint64_t n_max, double rows, cudaStream_t st);
+                    int B, int mode, uint32_t* touched, float* loss_out, float* pctr_out, float* abs_loss_sum,
+                    cudaStream_t st);
+// touched[j] (one entry per token position) = slot of the key first touched by token j, else 0xFFFFFFFF
+void xf_launch_update_touched(const XfTableView& t, const uint32_t* touched, uint64_t nnz, double rows,
+                              unsigned long long* unique_total, cudaStream_t st);
 void xf_launch_update_pushed(const XfTableView& t, const uint32_t* slots, uint64_t n, const float* gw,
                              const float* gv, cudaStream_t st);
-void xf_launch_batch_end(unsigned int* touched_cnt, unsigned long long* unique_total, cudaStream_t st);
 void xf_launch_probe(const XfTableView& t, const uint64_t* keys, uint64_t n, bool insert, uint32_t* slots,
                      float* w_out, cudaStream_t st);
 void xf_launch_gather_v(const XfTableView& t, const uint32_t* slots, const uint64_t* keys, uint64_t n,

@@ -1,0 +1,234 @@
+// The fused worker step (sm_100a): what LRWorker::update / FMWorker::update do between reading a
+// slice and returning from the last Push (src/model/lr/lr_worker.cc:121-177, fm/fm_worker.cc:126-245)
+// WITHOUT the reference's sort / unique / merge-join: the table row is the per-key accumulator.
+//
+//   CSR slice -> probe/insert every token's key (Pull semantics: missing keys are created)
+//             -> w (and for FM the latent row reduced to sum_k v, sum_k v^2) from the row just found
+//             -> per-row warp-segmented sums -> clamped sigmoid -> residual  (calculate_loss)
+//             -> every token adds its contribution to its key's gradient accumulators with L2
+//                atomics on the 32-byte sector it has just loaded                (calculate_gradient)
+//             -> the token that finds the "untouched" marker (-0.0) in g records the slot at its own
+//                position of the per-token `touched` array (no shared counter: a single contended
+//                append counter was measured to serialise the whole kernel); the optimizer kernel
+//                (kernels.cu) walks that array                                                (Push)
+//
+// One warp per row, one lane per token, two tokens per lane in flight: keys for a 64-token chunk are
+// loaded first, then the two first-probe sectors (one 256-bit load each), then resolved; the two
+// returning atomics of phase B are likewise issued back to back.  HBM / L2-latency bound integer and
+// float work on random sectors: no shared-memory tile, no tensor core — see DESIGN.md.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "table.cuh"
+
+#define XF_NO_SLOT 0xFFFFFFFFu
+#define XF_CACHED_CHUNKS 2  // 64-token chunks whose slots stay in registers (rows <= 128 tokens)
+
+template <int VEC>
+__device__ __forceinline__ void xf_ldv_step(const float* p, float (&o)[VEC]) {
+  if (VEC == 4) { float4 t = __ldcg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1 % VEC] = t.y; o[2 % VEC] = t.z; o[3 % VEC] = t.w; }
+  else if (VEC == 2) { float2 t = __ldcg(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1 % VEC] = t.y; }
+  else { o[0] = __ldcg(p); }
+}
+// vector reduction (no return value) into global memory: one L2 atomic transaction per 8 / 16 bytes
+template <int VEC>
+__device__ __forceinline__ void xf_redv_step(float* p, const float (&o)[VEC]) {
+  if (VEC == 4) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(o[0]), "f"(o[1 % VEC]),
+                 "f"(o[2 % VEC]), "f"(o[3 % VEC])
+                 : "memory");
+  } else if (VEC == 2) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(o[0]), "f"(o[1 % VEC]) : "memory");
+  } else {
+    atomicAdd(p, o[0]);
+  }
+}
+
+// FM: (sum_k v, sum_k v^2) of one token's latent row  (fm_worker.cc:178-192, per-token part)
+template <int VEC>
+__device__ __forceinline__ void xf_fm_token(const XfTableView& t, uint32_t slot, uint32_t flags, uint64_t key,
+                                            float& st, float& qt) {
+  const int K = t.K;
+  st = 0.f;
+  qt = 0.f;
+  if (flags & XF_FLAG_V_READY) {
+    const float* vp = reinterpret_cast<const float*>(xf_row(t, slot) + 32);
+    for (int k = 0; k < K; k += VEC) {
+      float v[VEC];
+      xf_ldv_step<VEC>(vp + k, v);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { st += v[e]; qt = __fadd_rn(qt, __fmul_rn(v[e], v[e])); }
+    }
+  } else {
+    for (int k = 0; k < K; ++k) {
+      const float v = xf_v_init(t, key, (uint32_t)k);
+      st += v;
+      qt = __fadd_rn(qt, __fmul_rn(v, v));
+    }
+  }
+}
+
+// FM: add loss * (S - v_k) to the token's latent-gradient accumulators  (fm_worker.cc:141-142)
+template <int VEC>
+__device__ __forceinline__ void xf_fm_token_grad(const XfTableView& t, uint32_t slot, uint64_t key, float loss, float S) {
+  const int K = t.K;
+  uint8_t* rowp = xf_row(t, slot);
+  const float* vp = xf_row_v(rowp);
+  float* gvp = xf_row_gv(rowp, K);
+  const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
+  const bool ready = (flags & XF_FLAG_V_READY) != 0;
+  for (int k = 0; k < K; k += VEC) {
+    float v[VEC], gc[VEC];
+    if (ready) {
+      xf_ldv_step<VEC>(vp + k, v);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[e] = xf_v_init(t, key, (uint32_t)(k + e));
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) gc[e] = __fmul_rn(loss, __fsub_rn(S, v[e]));
+    xf_redv_step<VEC>(gvp + k, gc);
+  }
+}
+
+//   mode: 0 = train, 1 = predict (forward only; the Pull still inserts missing keys, lr_worker.cc:47)
+template <bool FM, int VEC>
+__global__ void __launch_bounds__(256)
+xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* __restrict__ keys,
+          const uint8_t* __restrict__ labels, int B, int mode, uint32_t* __restrict__ touched,
+          float* __restrict__ loss_out, float* __restrict__ pctr_out, float* __restrict__ abs_loss_sum) {
+  __shared__ float s_abs[8];
+  float abs_acc = 0.f;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * warps_per_block;
+  const int K = t.K;
+
+  for (int row = gwarp; row < B; row += nwarps) {
+    const uint32_t beg = __ldg(row_ptr + row);
+    const uint32_t end = __ldg(row_ptr + row + 1);
+    const int chunks = (int)((end - beg + 63u) >> 6);
+
+    float wsum = 0.f, ssum = 0.f, qsum = 0.f;
+    uint32_t slot_c[2 * XF_CACHED_CHUNKS];
+#pragma unroll
+    for (int c = 0; c < 2 * XF_CACHED_CHUNKS; ++c) slot_c[c] = XF_NO_SLOT;
+
+    // ---------------- phase A: pull + per-token terms
+    for (int ch = 0; ch < chunks; ++ch) {
+      const uint32_t j0 = beg + (uint32_t)ch * 64u + (uint32_t)lane;
+      const uint32_t j1 = j0 + 32u;
+      const bool v0 = j0 < end, v1 = j1 < end;
+      const uint64_t k0 = v0 ? __ldg(keys + j0) : 0ull;
+      const uint64_t k1 = v1 ? __ldg(keys + j1) : 0ull;
+      const uint64_t p0 = xf_slot_hash(k0, t.log2cap), p1 = xf_slot_hash(k1, t.log2cap);
+      XfHead h0, h1;
+      h0.key = h1.key = XF_EMPTY_KEY;
+      if (v0) h0 = xf_load_head(xf_row(t, p0));
+      if (v1) h1 = xf_load_head(xf_row(t, p1));
+      uint32_t s0 = XF_NO_SLOT, s1 = XF_NO_SLOT;
+      if (v0) {
+        const int64_t r = xf_probe_from<true>(t, k0, p0, h0);
+        if (r >= 0) { s0 = (uint32_t)r; wsum += h0.w; }
+      }
+      if (v1) {
+        const int64_t r = xf_probe_from<true>(t, k1, p1, h1);
+        if (r >= 0) { s1 = (uint32_t)r; wsum += h1.w; }
+      }
+      if (FM) {
+        float st, qt;
+        if (s0 != XF_NO_SLOT) { xf_fm_token<VEC>(t, s0, h0.flags, k0, st, qt); ssum += st; qsum += qt; }
+        if (s1 != XF_NO_SLOT) { xf_fm_token<VEC>(t, s1, h1.flags, k1, st, qt); ssum += st; qsum += qt; }
+      }
+#pragma unroll
+      for (int c = 0; c < XF_CACHED_CHUNKS; ++c)
+        if (ch == c) { slot_c[2 * c] = s0; slot_c[2 * c + 1] = s1; }
+    }
+
+    // ---------------- per-row reduction, sigmoid, residual
+    const float wx = xf_warp_sum(wsum);
+    float S = 0.f, arg = wx;
+    if (FM) {
+      S = xf_warp_sum(ssum);
+      const float Q = xf_warp_sum(qsum);
+      const float v_y = __fsub_rn(__fmul_rn(S, S), Q);  // fm_worker.cc:193-196: no 1/2, collapsed over k
+      arg = __fadd_rn(wx, v_y);
+    }
+    const float pctr = xf_sigmoid(arg);
+    if (mode == 1) {
+      if (lane == 0 && pctr_out) pctr_out[row] = pctr;
+      continue;
+    }
+    const float loss = __fsub_rn(pctr, (float)labels[row]);  // lr_worker.cc:141 ; fm_worker.cc:200
+    if (lane == 0 && loss_out) loss_out[row] = loss;
+    abs_acc += fabsf(loss);
+
+    // ---------------- phase B: per-key gradient accumulation (the Push payload)
+    float gw_c = loss;
+    if (FM) {
+      // fm_worker.cc:140 accumulates the w-gradient inside the k loop: K sequential float adds
+      gw_c = 0.f;
+      for (int k = 0; k < K; ++k) gw_c += loss;
+    }
+    const double gw_d = (double)gw_c;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const uint32_t j0 = beg + (uint32_t)ch * 64u + (uint32_t)lane;
+      const uint32_t j1 = j0 + 32u;
+      uint32_t s0 = XF_NO_SLOT, s1 = XF_NO_SLOT;
+      if (ch < XF_CACHED_CHUNKS) {
+#pragma unroll
+        for (int c = 0; c < XF_CACHED_CHUNKS; ++c)
+          if (ch == c) { s0 = slot_c[2 * c]; s1 = slot_c[2 * c + 1]; }
+      } else {
+        XfHead h;
+        if (j0 < end) { const int64_t r = xf_probe<false>(t, __ldg(keys + j0), &h); if (r >= 0) s0 = (uint32_t)r; }
+        if (j1 < end) { const int64_t r = xf_probe<false>(t, __ldg(keys + j1), &h); if (r >= 0) s1 = (uint32_t)r; }
+      }
+      double old0 = 0.0, old1 = 0.0;
+      if (s0 != XF_NO_SLOT) old0 = atomicAdd(xf_row_g(xf_row(t, s0)), gw_d);
+      if (s1 != XF_NO_SLOT) old1 = atomicAdd(xf_row_g(xf_row(t, s1)), gw_d);
+      if (FM) {
+        if (s0 != XF_NO_SLOT) xf_fm_token_grad<VEC>(t, s0, __ldg(keys + j0), loss, S);
+        if (s1 != XF_NO_SLOT) xf_fm_token_grad<VEC>(t, s1, __ldg(keys + j1), loss, S);
+      }
+      const bool f0 = s0 != XF_NO_SLOT && (unsigned long long)__double_as_longlong(old0) == XF_NEG_ZERO_BITS64;
+      const bool f1 = s1 != XF_NO_SLOT && (unsigned long long)__double_as_longlong(old1) == XF_NEG_ZERO_BITS64;
+      if (j0 < end) touched[j0] = f0 ? s0 : XF_NO_SLOT;
+      if (j1 < end) touched[j1] = f1 ? s1 : XF_NO_SLOT;
+    }
+  }
+  // monitoring scalar: sum over rows of |pctr - label| (one atomic per block)
+  if (abs_loss_sum != nullptr && mode == 0) {
+    if (lane == 0) s_abs[threadIdx.x >> 5] = abs_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_abs[w];
+      atomicAdd(abs_loss_sum, tot);
+    }
+  }
+}
+
+int xf_sms();
+int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm);
+
+void xf_launch_step(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* labels,
+                    int B, int mode, uint32_t* touched, float* loss_out, float* pctr_out, float* abs_loss_sum,
+                    cudaStream_t st) {
+  if (B <= 0) return;
+  const int block = 256;
+  const int grid = xf_grid_for((uint64_t)B * 32, block, 8);
+#define XF_STEP_ARGS t, row_ptr, keys, labels, B, mode, touched, loss_out, pctr_out, abs_loss_sum
+  if (t.K == 0) {
+    xf_k_step<false, 1><<<grid, block, 0, st>>>(XF_STEP_ARGS);
+  } else {
+    switch (xf_vec_for(t.K)) {
+      case 4: xf_k_step<true, 4><<<grid, block, 0, st>>>(XF_STEP_ARGS); break;
+      case 2: xf_k_step<true, 2><<<grid, block, 0, st>>>(XF_STEP_ARGS); break;
+      default: xf_k_step<true, 1><<<grid, block, 0, st>>>(XF_STEP_ARGS); break;
+    }
+  }
+#undef XF_STEP_ARGS
+}

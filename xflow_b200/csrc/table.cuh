@@ -112,36 +112,40 @@ struct XfHead {
 };
 
 __device__ __forceinline__ XfHead xf_load_head(const uint8_t* row) {
-  // one 32-byte sector, two 16-byte L2 loads (L1 is useless for random rows)
-  uint4 a = __ldcg(reinterpret_cast<const uint4*>(row));
-  uint4 b = __ldcg(reinterpret_cast<const uint4*>(row + 16));
+  // one 32-byte sector = ONE 256-bit L2 load (sm_100 LDG.E.256; L1 is useless for random rows).
+  // Two 16-byte loads cost two L2 requests and, measured with ncu, up to two DRAM fetches.
+  uint64_t q0, q1, q2, q3;
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(row));
   XfHead h;
-  h.key = (uint64_t)a.x | ((uint64_t)a.y << 32);
-  h.w = __uint_as_float(a.z);
-  h.n = __uint_as_float(a.w);
-  h.z = __uint_as_float(b.x);
-  h.flags = b.y;
-  h.g = __longlong_as_double((long long)((uint64_t)b.z | ((uint64_t)b.w << 32)));
+  h.key = q0;
+  h.w = __uint_as_float((uint32_t)q1);
+  h.n = __uint_as_float((uint32_t)(q1 >> 32));
+  h.z = __uint_as_float((uint32_t)q2);
+  h.flags = (uint32_t)(q2 >> 32);
+  h.g = __longlong_as_double((long long)q3);
   return h;
 }
 
-// Find `key`; if INSERT, claim an empty slot for it when absent (store[key] semantics).
-// Returns the slot index, or -1 (not found without INSERT, or probe overflow -> *t.error = 1).
-// `head` receives the row's first sector as it was when the key matched (or defaults on insert).
+// full-sector store of the head (one 256-bit STG: no partial-sector write, no read-for-fill)
+__device__ __forceinline__ void xf_store_head(uint8_t* row, const XfHead& h) {
+  const uint64_t q1 = (uint64_t)__float_as_uint(h.w) | ((uint64_t)__float_as_uint(h.n) << 32);
+  const uint64_t q2 = (uint64_t)__float_as_uint(h.z) | ((uint64_t)h.flags << 32);
+  const uint64_t q3 = (uint64_t)__double_as_longlong(h.g);
+  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(row), "l"(h.key), "l"(q1), "l"(q2), "l"(q3) : "memory");
+}
+
+// Find `key` starting at slot `s` whose head `h` the caller has already loaded; if INSERT, claim an
+// empty slot for it when absent (store[key] semantics).  Returns the slot index, or -1 (not found
+// without INSERT, or probe overflow -> *t.error = 1).  On return `h` is the row's first sector as it
+// was when the key matched (or the default contents on insert).
 template <bool INSERT>
-__device__ __forceinline__ int64_t xf_probe(const XfTableView& t, uint64_t key, XfHead* head) {
-  uint64_t s = xf_slot_hash(key, t.log2cap);
+__device__ __forceinline__ int64_t xf_probe_from(const XfTableView& t, uint64_t key, uint64_t s, XfHead& h) {
   for (int probes = 0; probes < XF_MAX_PROBE; ++probes) {
-    uint8_t* row = xf_row(t, s);
-    XfHead h = xf_load_head(row);
-    if (h.key == key) {
-      *head = h;
-      return (int64_t)s;
-    }
+    if (h.key == key) return (int64_t)s;
     if (h.key == XF_EMPTY_KEY) {
       if (!INSERT) return -1;
       unsigned long long old =
-          atomicCAS(reinterpret_cast<unsigned long long*>(row), (unsigned long long)XF_EMPTY_KEY,
+          atomicCAS(reinterpret_cast<unsigned long long*>(xf_row(t, s)), (unsigned long long)XF_EMPTY_KEY,
                     (unsigned long long)key);
       if (old == XF_EMPTY_KEY) {
         // we created the entry: count it (warp-aggregated) and report default contents
@@ -149,21 +153,29 @@ __device__ __forceinline__ int64_t xf_probe(const XfTableView& t, uint64_t key, 
         int leader = __ffs(m) - 1;
         if ((int)(threadIdx.x & 31) == leader) atomicAdd(t.size, (unsigned long long)__popc(m));
         h.key = key; h.flags = 0; h.w = 0.f; h.n = 0.f; h.z = 0.f; h.g = -0.0;
-        *head = h;
         return (int64_t)s;
       }
       if (old == key) {
         // raced with another inserter of the same key: the parameter fields are still defaults
         h.key = key;
-        *head = h;
         return (int64_t)s;
       }
       // a different key took the slot: fall through to the next one
     }
     s = (s + 1) & t.mask;
+    h = xf_load_head(xf_row(t, s));
   }
   *t.error = 1;
   return -1;
+}
+
+template <bool INSERT>
+__device__ __forceinline__ int64_t xf_probe(const XfTableView& t, uint64_t key, XfHead* head) {
+  const uint64_t s = xf_slot_hash(key, t.log2cap);
+  XfHead h = xf_load_head(xf_row(t, s));
+  const int64_t r = xf_probe_from<INSERT>(t, key, s, h);
+  *head = h;
+  return r;
 }
 
 // ---- arithmetic restated from the reference, IEEE-rounded op by op (no FMA contraction) ----
