@@ -73,6 +73,8 @@ def lib():
     L.xo_predict.argtypes = [vp, vp, vp, i64, vp]
     L.xo_auc_logloss.argtypes = [vp, vp, i64, vp]
     L.xo_set_exact_sums.argtypes = [C.c_int]
+    L.xo_worker_compute_given.restype = i64
+    L.xo_worker_compute_given.argtypes = [C.c_int, vp, vp, vp, i64, vp, vp]
     _lib = L
     return L
 
@@ -215,6 +217,23 @@ class exact_sums:
 
     def __exit__(self, *a):
         lib().xo_set_exact_sums(0)
+
+
+def worker_compute_given(K, row_ptr, keys, labels, w, v=None):
+    """calculate_loss + calculate_gradient with externally pulled values for the SORTED unique keys.
+    Returns (gw[U], gv[U,K], loss[B])."""
+    row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+    keys = np.ascontiguousarray(keys, np.uint64)
+    labels = np.ascontiguousarray(labels, np.int32)
+    w = np.ascontiguousarray(w, np.float32)
+    v = None if v is None else np.ascontiguousarray(v, np.float32)
+    B = labels.size
+    U = lib().xo_worker_compute_given(K, _p(row_ptr), _p(keys), _p(labels), B, _p(w), _p(v))
+    gw = np.empty(U, np.float32)
+    gv = np.empty((U, K), np.float32)
+    loss = np.empty(B, np.float32)
+    lib().xo_worker_get(None, _p(gw), _p(gv) if K else None, _p(loss))
+    return gw, gv, loss
 
 
 def auc_logloss(labels, pctr):

@@ -705,7 +705,7 @@ XF_DLL int xf_trainer_stats(xf_trainer* tr, uint64_t* steps, uint64_t* rows, uin
     unsigned long long u = 0;
     XF_CUDA_TRY(cudaMemcpyAsync(&u, tr->d_unique_total, sizeof(u), cudaMemcpyDeviceToHost, tr->table->stream));
     XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
-    *unique_keys = u;
+    *unique_keys = u + tr->host_unique;
   }
   return XF_OK;
 }

@@ -86,6 +86,7 @@ struct xf_trainer {
   float* d_abs_loss = nullptr;          // 2 slots
   float* h_abs_loss = nullptr;          // pinned, 2 slots
   uint64_t n_steps = 0, n_rows = 0, n_nnz = 0;
+  uint64_t host_unique = 0;             // unique keys counted on the host (sharded path)
   uint32_t last_rows = 0;
   uint64_t launches = 0;
   void* mg = nullptr;                   // multi-GPU exchange state (comm.cu)

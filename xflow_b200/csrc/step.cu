@@ -121,8 +121,8 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
       const uint32_t j0 = beg + (uint32_t)ch * 64u + (uint32_t)lane;
       const uint32_t j1 = j0 + 32u;
       const bool v0 = j0 < end, v1 = j1 < end;
-      const uint64_t k0 = v0 ? __ldg(keys + j0) : 0ull;
-      const uint64_t k1 = v1 ? __ldg(keys + j1) : 0ull;
+      const uint64_t k0 = v0 ? __ldcs(keys + j0) : 0ull;  // streaming: do not displace table sectors in L2
+      const uint64_t k1 = v1 ? __ldcs(keys + j1) : 0ull;
       const uint64_t p0 = xf_slot_hash(k0, t.log2cap), p1 = xf_slot_hash(k1, t.log2cap);
       XfHead h0, h1;
       h0.key = h1.key = XF_EMPTY_KEY;
@@ -195,8 +195,8 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
       }
       const bool f0 = s0 != XF_NO_SLOT && (unsigned long long)__double_as_longlong(old0) == XF_NEG_ZERO_BITS64;
       const bool f1 = s1 != XF_NO_SLOT && (unsigned long long)__double_as_longlong(old1) == XF_NEG_ZERO_BITS64;
-      if (j0 < end) touched[j0] = f0 ? s0 : XF_NO_SLOT;
-      if (j1 < end) touched[j1] = f1 ? s1 : XF_NO_SLOT;
+      if (j0 < end) __stcs(touched + j0, f0 ? s0 : XF_NO_SLOT);
+      if (j1 < end) __stcs(touched + j1, f1 ? s1 : XF_NO_SLOT);
     }
   }
   // monitoring scalar: sum over rows of |pctr - label| (one atomic per block)
