@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or not os.path.exists(LIB):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lnccl", "-lpthread"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lpthread", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

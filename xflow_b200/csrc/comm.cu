@@ -21,7 +21,8 @@
 //
 // The three all-to-alls are grouped ncclSend/ncclRecv on the table's stream.  NVSwitch gives every
 // pair the same bandwidth, so a flat all-to-all is the right schedule; at S = 1 none of this runs.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library itself is bound at run time, see XfNccl
 #include <stdio.h>
 #include <string.h>
 
@@ -29,11 +30,52 @@
 
 #include "internal.h"
 
+// NCCL is bound with dlopen at the first xf_comm_* call instead of at link time.  A process that also
+// hosts PyTorch already has PyTorch's own (newer) libnccl.so.2 mapped; linking ours against the system
+// copy made whichever library loaded second fail on missing symbols.  RTLD_NOLOAD first reuses an
+// already-mapped libnccl.so.2, otherwise the system one is loaded (plain C++ hosts).
+struct XfNccl {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+static XfNccl g_nccl;
+
+static int xf_nccl_bind() {
+  if (g_nccl.ok) return XF_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    xf_set_error("cannot load libnccl.so.2: %s", dlerror());
+    return XF_ERR_COMM;
+  }
+#define XF_BIND(name)                                                         \
+  g_nccl.name = reinterpret_cast<decltype(g_nccl.name)>(dlsym(h, "nccl" #name)); \
+  if (!g_nccl.name) {                                                         \
+    xf_set_error("libnccl lacks nccl" #name);                                 \
+    return XF_ERR_COMM;                                                       \
+  }
+  XF_BIND(GetUniqueId) XF_BIND(CommInitRank) XF_BIND(CommDestroy) XF_BIND(AllReduce) XF_BIND(AllGather)
+  XF_BIND(Send) XF_BIND(Recv) XF_BIND(GroupStart) XF_BIND(GroupEnd) XF_BIND(GetErrorString)
+#undef XF_BIND
+  g_nccl.ok = true;
+  return XF_OK;
+}
+
 #define XF_NCCL_TRY(expr)                                                                        \
   do {                                                                                           \
     ncclResult_t _r = (expr);                                                                    \
     if (_r != ncclSuccess) {                                                                     \
-      xf_set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, ncclGetErrorString(_r));       \
+      xf_set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(_r));       \
       return XF_ERR_COMM;                                                                        \
     }                                                                                            \
   } while (0)
@@ -47,8 +89,9 @@ static_assert(sizeof(ncclUniqueId) <= XF_COMM_ID_BYTES, "ncclUniqueId does not f
 
 XF_DLL int xf_comm_get_id(uint8_t id[XF_COMM_ID_BYTES]) {
   if (!id) return XF_ERR_ARG;
+  XF_TRY(xf_nccl_bind());
   ncclUniqueId uid;
-  XF_NCCL_TRY(ncclGetUniqueId(&uid));
+  XF_NCCL_TRY(g_nccl.GetUniqueId(&uid));
   memset(id, 0, XF_COMM_ID_BYTES);
   memcpy(id, &uid, sizeof(uid));
   return XF_OK;
@@ -56,6 +99,7 @@ XF_DLL int xf_comm_get_id(uint8_t id[XF_COMM_ID_BYTES]) {
 
 XF_DLL int xf_comm_create(xf_comm** out, const uint8_t id[XF_COMM_ID_BYTES], int rank, int nranks, int device) {
   if (!out || !id || nranks < 1 || rank < 0 || rank >= nranks) return XF_ERR_ARG;
+  XF_TRY(xf_nccl_bind());
   XF_CUDA_TRY(cudaSetDevice(device));
   xf_comm* c = new xf_comm;
   c->rank = rank;
@@ -63,9 +107,9 @@ XF_DLL int xf_comm_create(xf_comm** out, const uint8_t id[XF_COMM_ID_BYTES], int
   c->device = device;
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof(uid));
-  ncclResult_t r = ncclCommInitRank(&c->nccl, nranks, uid, rank);
+  ncclResult_t r = g_nccl.CommInitRank(&c->nccl, nranks, uid, rank);
   if (r != ncclSuccess) {
-    xf_set_error("ncclCommInitRank failed: %s", ncclGetErrorString(r));
+    xf_set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
     delete c;
     return XF_ERR_COMM;
   }
@@ -75,7 +119,7 @@ XF_DLL int xf_comm_create(xf_comm** out, const uint8_t id[XF_COMM_ID_BYTES], int
 
 XF_DLL int xf_comm_destroy(xf_comm* c) {
   if (!c) return XF_OK;
-  if (c->nccl) ncclCommDestroy(c->nccl);
+  if (c->nccl) g_nccl.CommDestroy(c->nccl);
   delete c;
   return XF_OK;
 }
@@ -89,7 +133,7 @@ XF_DLL int xf_comm_barrier(xf_comm* c) {
   int* d = nullptr;
   XF_CUDA_TRY(cudaMalloc(&d, sizeof(int)));
   XF_CUDA_TRY(cudaMemset(d, 0, sizeof(int)));
-  XF_NCCL_TRY(ncclAllReduce(d, d, 1, ncclInt, ncclSum, c->nccl, 0));
+  XF_NCCL_TRY(g_nccl.AllReduce(d, d, 1, ncclInt, ncclSum, c->nccl, 0));
   XF_CUDA_TRY(cudaStreamSynchronize(0));
   cudaFree(d);
   return XF_OK;
@@ -317,16 +361,16 @@ int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm);
 static int xf_all_to_all(xf_comm* c, const void* send, const std::vector<uint64_t>& soff,
                          const std::vector<uint64_t>& scnt, void* recv, const std::vector<uint64_t>& roff,
                          const std::vector<uint64_t>& rcnt, size_t elem_bytes, size_t scale, cudaStream_t st) {
-  XF_NCCL_TRY(ncclGroupStart());
+  XF_NCCL_TRY(g_nccl.GroupStart());
   for (int q = 0; q < c->nranks; ++q) {
     if (scnt[q])
-      XF_NCCL_TRY(ncclSend((const char*)send + soff[q] * scale * elem_bytes, scnt[q] * scale * elem_bytes, ncclChar, q,
+      XF_NCCL_TRY(g_nccl.Send((const char*)send + soff[q] * scale * elem_bytes, scnt[q] * scale * elem_bytes, ncclChar, q,
                            c->nccl, st));
     if (rcnt[q])
-      XF_NCCL_TRY(ncclRecv((char*)recv + roff[q] * scale * elem_bytes, rcnt[q] * scale * elem_bytes, ncclChar, q,
+      XF_NCCL_TRY(g_nccl.Recv((char*)recv + roff[q] * scale * elem_bytes, rcnt[q] * scale * elem_bytes, ncclChar, q,
                            c->nccl, st));
   }
-  XF_NCCL_TRY(ncclGroupEnd());
+  XF_NCCL_TRY(g_nccl.GroupEnd());
   return XF_OK;
 }
 
@@ -355,7 +399,7 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
     XF_CUDA_TRY(cudaMemsetAsync(mg->send_counts.p, 0, (size_t)S * 4, st));
   }
   // ---- bucket sizes of every rank (the only host sync of the step)
-  XF_NCCL_TRY(ncclAllGather(mg->send_counts.p, mg->all_counts.p, (size_t)S, ncclUint32, c->nccl, st));
+  XF_NCCL_TRY(g_nccl.AllGather(mg->send_counts.p, mg->all_counts.p, (size_t)S, ncclUint32, c->nccl, st));
   XF_CUDA_TRY(cudaMemcpyAsync(mg->h_counts, mg->all_counts.p, (size_t)S * S * 4, cudaMemcpyDeviceToHost, st));
   XF_CUDA_TRY(cudaStreamSynchronize(st));
   uint64_t n_send = 0, n_recv = 0;
