@@ -17,7 +17,7 @@ OBJDIR = os.path.join(ROOT, "build", "obj")
 
 CU_SOURCES = ["kernels.cu", "step.cu", "capi.cu", "comm.cu", "ingest.cu"]
 CC_SOURCES = ["loader.cc", "metrics.cc", "worker.cc"]
-HEADERS = ["table.cuh", "kernels.h", "internal.h", "hash.h", os.path.join(ROOT, "include", "xflow_b200.h"),
+HEADERS = ["table.cuh", "workset.cuh", "kernels.h", "internal.h", "hash.h", os.path.join(ROOT, "include", "xflow_b200.h"),
            os.path.join(ROOT, "include", "xflow", "xflow.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

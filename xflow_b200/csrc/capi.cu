@@ -543,32 +543,36 @@ static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const 
                                const uint8_t* d_labels, uint32_t rows, uint32_t nnz, int mode, float* d_abs) {
   xf_table* t = tr->table;
   if (rows == 0) return XF_OK;
-  if (tr->mg) return xf_mg_step(tr, d_row_ptr, d_keys, d_labels, rows, nnz, mode, d_abs);
-  XF_TRY(t->ensure_room(nnz));
+  if (!tr->mg) XF_TRY(t->ensure_room(nnz));  // the sharded path sizes the shard from what it receives
   cudaStream_t st = t->stream;
   const bool prof = tr->profile && mode == 0;
   cudaEvent_t* pe = nullptr;
+  if (tr->mg && !prof) return xf_mg_step(tr, d_row_ptr, d_keys, d_labels, rows, nnz, mode, d_abs, nullptr);
   if (prof) {
-    if (tr->prof_used + 3 > tr->prof_events.size()) {
+    if (tr->prof_used + 4 > tr->prof_events.size()) {
       size_t old = tr->prof_events.size();
-      tr->prof_events.resize(old + 3 * 256);
+      tr->prof_events.resize(old + 4 * 256);
       for (size_t i = old; i < tr->prof_events.size(); ++i) XF_CUDA_TRY(cudaEventCreate(&tr->prof_events[i]));
     }
     pe = &tr->prof_events[tr->prof_used];
-    tr->prof_used += 3;
+    tr->prof_used += 4;
+    if (tr->mg) return xf_mg_step(tr, d_row_ptr, d_keys, d_labels, rows, nnz, mode, d_abs, pe);
     XF_CUDA_TRY(cudaEventRecord(pe[0], st));
   }
   xf_launch_step(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
                  (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
                  mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
   ++tr->launches;
-  if (prof) XF_CUDA_TRY(cudaEventRecord(pe[1], st));
+  if (prof) {
+    XF_CUDA_TRY(cudaEventRecord(pe[1], st));
+    XF_CUDA_TRY(cudaEventRecord(pe[2], st));
+  }
   if (mode == 0) {
     // Push + server-side optimizer: one FTRL/SGD step per touched key with g / rows
     xf_launch_update_touched(t->view, tr->touched.as<uint32_t>(), nnz, (double)rows, tr->d_unique_total, st);
     ++tr->launches;
   }
-  if (prof) XF_CUDA_TRY(cudaEventRecord(pe[2], st));
+  if (prof) XF_CUDA_TRY(cudaEventRecord(pe[3], st));
   XF_CUDA_TRY(cudaGetLastError());
   return XF_OK;
 }
@@ -770,14 +774,14 @@ XF_DLL int xf_trainer_profile(xf_trainer* tr, double ms[2], uint64_t* steps) {
   if (!tr || !ms) return XF_ERR_ARG;
   XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
   ms[0] = ms[1] = 0.0;
-  for (size_t i = 0; i + 3 <= tr->prof_used; i += 3) {
+  for (size_t i = 0; i + 4 <= tr->prof_used; i += 4) {
     float a = 0.f, b = 0.f;
     XF_CUDA_TRY(cudaEventElapsedTime(&a, tr->prof_events[i], tr->prof_events[i + 1]));
-    XF_CUDA_TRY(cudaEventElapsedTime(&b, tr->prof_events[i + 1], tr->prof_events[i + 2]));
+    XF_CUDA_TRY(cudaEventElapsedTime(&b, tr->prof_events[i + 2], tr->prof_events[i + 3]));
     ms[0] += a;
     ms[1] += b;
   }
-  if (steps) *steps = tr->prof_used / 3;
+  if (steps) *steps = tr->prof_used / 4;
   tr->prof_used = 0;
   return XF_OK;
 }

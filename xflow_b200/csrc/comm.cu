@@ -6,14 +6,13 @@
 // Every rank is at once a WORKER (its own CSR batch) and the SERVER of one key range
 // (shard = min(key / floor((2^64-1)/S), S-1), postoffice.cc:134-143).  One step =
 //
-//   worker  dedup the batch's keys into a small per-batch cache table (same row layout as the main
-//           table), bucket the unique keys by owner                       [xf_k_mg_dedup, _scan, _scatter]
+//   worker  dedup the batch's keys into the per-batch work set (workset.cuh): every unique key gets a
+//           number u inside its owner's bucket                            [xf_k_ws_dedup]
 //   all     exchange bucket sizes (ncclAllGather), then keys              [all-to-all #1 = the Pull request]
 //   owner   probe/insert the received keys in its shard, gather w (,v)    [xf_k_probe, xf_k_gather_v]
-//   all     values back                                                   [all-to-all #2 = the Pull response]
-//   worker  load them into the cache rows; run THE SAME fused step kernel as the single-GPU path
-//           against the cache table (forward, residual, per-key gradient accumulation)
-//           gather g / rows per unique key, clear the cache rows          [xf_k_mg_fill, xf_k_step, xf_k_mg_grads]
+//   all     values back, straight into the work set's compact arrays      [all-to-all #2 = the Pull response]
+//   worker  the fused step against the work set (same arithmetic as the single-GPU kernel: forward,
+//           residual, per-key gradient accumulation), then g / rows       [xf_k_step_ws, xf_k_ws_grads]
 //   all     gradients to the owners                                       [all-to-all #3 = the Push]
 //   owner   one FTRL/SGD step per (source rank, key), source ranks applied in rank order — one legal
 //           schedule of the reference's asynchronous multi-worker run (every worker pulled before any
@@ -24,6 +23,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: the library itself is bound at run time, see XfNccl
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -142,141 +142,87 @@ XF_DLL int xf_comm_barrier(xf_comm* c) {
 // -------------------------------------------------------------------------------------------------
 // worker-side kernels of the sharded step
 // -------------------------------------------------------------------------------------------------
-#define XF_MG_BLOCK 256
 #define XF_MG_MAX_SHARDS 16
-#define XF_NONE 0xFFFFFFFFu
+#define XF_WS_BLOCK 1024
+#define XF_WS_TOK 4  // tokens per thread
 
 __device__ __forceinline__ int xf_dev_shard_of(uint64_t key, uint64_t width, int S) {
   const uint64_t s = key / width;
   return (int)(s < (uint64_t)S ? s : (uint64_t)S - 1);
 }
 
-// Token j -> cache row of its key (inserted on first sight).  first[j] = cache slot if token j is the
-// one that created the entry (so unique keys are exactly the tokens with first[j] != NONE), and the
-// block counts its creators per owner shard.  Block b owns tokens [b*chunk, (b+1)*chunk).
-__global__ void __launch_bounds__(XF_MG_BLOCK)
-xf_k_mg_dedup(XfTableView wc, const uint64_t* __restrict__ keys, uint32_t nnz, uint32_t chunk, uint64_t width, int S,
-              uint32_t* __restrict__ first, uint32_t* __restrict__ blk_counts) {
+// Insert every token's key into the work set; the token that claims a key first numbers it inside
+// its owner's bucket (block-aggregated reservation: one global atomic per block and shard) and lists
+// it in ws.keys.  Buckets are contiguous: u = shard * cap + position.
+__global__ void __launch_bounds__(XF_WS_BLOCK)
+xf_k_ws_dedup(XfWorkSet ws, const uint64_t* __restrict__ keys, uint32_t nnz, uint64_t width, int S,
+              uint32_t* __restrict__ bucket_cnt) {
   __shared__ unsigned int s_cnt[XF_MG_MAX_SHARDS];
+  __shared__ unsigned int s_base[XF_MG_MAX_SHARDS];
   if (threadIdx.x < XF_MG_MAX_SHARDS) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t lo = blockIdx.x * chunk;
-  const uint32_t hi = min(nnz, lo + chunk);
-  for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
-    const uint64_t key = keys[j];
-    const uint64_t p = xf_slot_hash(key, wc.log2cap);
-    XfHead h = xf_load_head(xf_row(wc, p));
-    const int64_t s = xf_probe_from<true>(wc, key, p, h);
-    uint32_t mine = XF_NONE;
-    if (s >= 0) {
-      // claim "I list this key": flags bit 1, exactly one token wins per key and batch
-      unsigned int* fl = reinterpret_cast<unsigned int*>(xf_row(wc, (uint64_t)s) + XF_OFF_FLAGS);
-      const unsigned int old = atomicOr(fl, 2u);
-      if ((old & 2u) == 0u) {
-        mine = (uint32_t)s;
-        atomicAdd(&s_cnt[xf_dev_shard_of(key, width, S)], 1u);
-      }
+  const uint32_t j_base = blockIdx.x * (XF_WS_BLOCK * XF_WS_TOK) + threadIdx.x;
+  uint64_t my_key[XF_WS_TOK];
+  uint64_t my_slot[XF_WS_TOK];
+  uint32_t my_local[XF_WS_TOK];  // position inside the block's share of the bucket, or NONE
+#pragma unroll
+  for (int i = 0; i < XF_WS_TOK; ++i) {
+    const uint32_t j = j_base + i * XF_WS_BLOCK;
+    my_local[i] = 0xFFFFFFFFu;
+    my_key[i] = (j < nnz) ? __ldcs(keys + j) : 0xFFFFFFFFFFFFFFFFull;
+  }
+#pragma unroll
+  for (int i = 0; i < XF_WS_TOK; ++i) {
+    const uint64_t key = my_key[i];
+    if (key == 0xFFFFFFFFFFFFFFFFull) continue;
+    uint64_t s = xf_ws_hash(key, ws.log2cap);
+    for (int probes = 0; probes < 8192; ++probes) {
+      unsigned long long* kp = reinterpret_cast<unsigned long long*>(ws.set + s * 16);
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
+      if (cur == 0xFFFFFFFFFFFFFFFFull) cur = atomicCAS(kp, 0xFFFFFFFFFFFFFFFFull, (unsigned long long)key);
+      if (cur == 0xFFFFFFFFFFFFFFFFull || cur == key) break;
+      s = (s + 1) & ws.mask;
     }
-    first[j] = mine;
-  }
-  __syncthreads();
-  if (threadIdx.x < S) blk_counts[blockIdx.x * S + threadIdx.x] = s_cnt[threadIdx.x];
-}
-
-// one block: exclusive scan of blk_counts over blocks, per shard; bucket totals and bucket bases
-__global__ void xf_k_mg_scan(const uint32_t* __restrict__ blk_counts, uint32_t nblk, int S,
-                             uint32_t* __restrict__ blk_offsets, uint32_t* __restrict__ send_counts) {
-  __shared__ uint32_t s_tot[XF_MG_MAX_SHARDS];
-  const int sh = threadIdx.x;
-  if (sh < S) {
-    uint32_t run = 0;
-    for (uint32_t b = 0; b < nblk; ++b) {
-      const uint32_t c = blk_counts[b * S + sh];
-      blk_offsets[b * S + sh] = run;
-      run += c;
+    // claim: exactly one token per key sees "unclaimed"
+    const unsigned int old = atomicExch(reinterpret_cast<unsigned int*>(ws.set + s * 16 + 12), 0u);
+    if (old == 0xFFFFFFFFu) {
+      my_slot[i] = s;
+      my_local[i] = atomicAdd(&s_cnt[xf_dev_shard_of(key, width, S)], 1u);
     }
-    s_tot[sh] = run;
-    send_counts[sh] = run;
   }
   __syncthreads();
-  if (sh < S) {
-    uint32_t base = 0;
-    for (int q = 0; q < sh; ++q) base += s_tot[q];
-    for (uint32_t b = 0; b < nblk; ++b) blk_offsets[b * S + sh] += base;
+  if (threadIdx.x < S && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(bucket_cnt + threadIdx.x, s_cnt[threadIdx.x]);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < XF_WS_TOK; ++i) {
+    if (my_local[i] == 0xFFFFFFFFu) continue;
+    const int q = xf_dev_shard_of(my_key[i], width, S);
+    const uint32_t u = (uint32_t)q * ws.cap + s_base[q] + my_local[i];
+    ws.keys[u] = my_key[i];
+    *reinterpret_cast<uint32_t*>(ws.set + my_slot[i] * 16 + 8) = u;
   }
 }
 
-// creators write (key, cache slot) into their owner's bucket of the send list
-__global__ void __launch_bounds__(XF_MG_BLOCK)
-xf_k_mg_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ first, uint32_t nnz, uint32_t chunk,
-                uint64_t width, int S, const uint32_t* __restrict__ blk_offsets, uint64_t* __restrict__ send_keys,
-                uint32_t* __restrict__ send_slot) {
-  __shared__ unsigned int s_pos[XF_MG_MAX_SHARDS];
-  if (threadIdx.x < S) s_pos[threadIdx.x] = blk_offsets[blockIdx.x * S + threadIdx.x];
-  __syncthreads();
-  const uint32_t lo = blockIdx.x * chunk;
-  const uint32_t hi = min(nnz, lo + chunk);
-  for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
-    const uint32_t s = first[j];
-    if (s == XF_NONE) continue;
-    const uint64_t key = keys[j];
-    const uint32_t pos = atomicAdd(&s_pos[xf_dev_shard_of(key, width, S)], 1u);
-    send_keys[pos] = key;
-    send_slot[pos] = s;
-  }
-}
-
-// pulled values -> cache rows (w into the head, v block + V_READY)
-__global__ void xf_k_mg_fill(XfTableView wc, const uint32_t* __restrict__ send_slot, uint32_t n,
-                             const float* __restrict__ w, const float* __restrict__ v) {
-  const int K = wc.K;
+// per unique key: gradient sums / rows -> Push payload; accumulators back to zero (streaming pass)
+__global__ void xf_k_ws_grads(XfWorkSet ws, XfBucketCounts cnt, double rows, int want_grads,
+                              float* __restrict__ grad_w, float* __restrict__ grad_v) {
+  const int q = blockIdx.y;
+  const uint32_t n = cnt.c[q];
+  const int K = ws.K;
   const uint64_t per = (uint64_t)K + 1;
   const uint64_t total = (uint64_t)n * per;
-  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total;
-       x += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t i = x / per;
-    const int c = (int)(x % per);
-    uint8_t* rowp = xf_row(wc, send_slot[i]);
-    if (c == 0) {
-      *reinterpret_cast<float*>(rowp + 8) = w[i];
-      *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = 2u | (K > 0 ? XF_FLAG_V_READY : 0u);
+  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (uint64_t)gridDim.x * blockDim.x) {
+    // coordinate-major inside the bucket keeps both arrays coalesced
+    if (x < n) {
+      const uint64_t u = (uint64_t)q * ws.cap + x;
+      if (want_grads) grad_w[u] = xf_div_rows((float)ws.gw[u], rows);  // lr_worker.cc:116-118
+      ws.gw[u] = 0.0;
     } else {
-      xf_row_v(rowp)[c - 1] = v[i * K + (c - 1)];
+      const uint64_t y = x - n;  // in [0, n*K)
+      const uint64_t idx = (uint64_t)q * ws.cap * K + y;
+      if (want_grads) grad_v[idx] = xf_div_rows(ws.gv[idx], rows);     // fm_worker.cc:154-156
+      ws.gv[idx] = 0.f;
     }
-  }
-}
-
-// per unique key: gradient sums / rows -> send arrays (what the worker Pushes), then reset the cache row
-__global__ void xf_k_mg_grads(XfTableView wc, const uint32_t* __restrict__ send_slot, uint32_t n, double rows,
-                              int want_grads, float* __restrict__ gw, float* __restrict__ gv) {
-  const int K = wc.K;
-  const uint64_t per = (uint64_t)K + 1;
-  const uint64_t total = (uint64_t)n * per;
-  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total;
-       x += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t i = x / per;
-    const int c = (int)(x % per);
-    uint8_t* rowp = xf_row(wc, send_slot[i]);
-    if (c == 0) {
-      if (want_grads) {
-        const double g = *reinterpret_cast<const double*>(rowp + 24);
-        gw[i] = xf_div_rows((float)g, rows);  // lr_worker.cc:116-118
-      }
-    } else {
-      float* gp = xf_row_gv(rowp, K) + (c - 1);
-      if (want_grads) gv[i * K + (c - 1)] = xf_div_rows(*gp, rows);  // fm_worker.cc:154-156
-      *gp = 0.f;
-    }
-  }
-}
-
-// second pass of the reset (separate kernel: the head may only be cleared once every coordinate
-// thread of xf_k_mg_grads has read it)
-__global__ void xf_k_mg_clear(XfTableView wc, const uint32_t* __restrict__ send_slot, uint32_t n) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    XfHead h;
-    h.key = XF_EMPTY_KEY; h.flags = 0; h.w = 0.f; h.n = 0.f; h.z = 0.f; h.g = -0.0;
-    xf_store_head(xf_row(wc, send_slot[i]), h);
   }
 }
 
@@ -286,14 +232,22 @@ __global__ void xf_k_mg_clear(XfTableView wc, const uint32_t* __restrict__ send_
 struct XfMg {
   int S = 1, rank = 0;
   uint64_t width = 0;
-  xf_table* wc = nullptr;              // per-batch worker cache table
-  uint32_t chunk = 0, nblk = 0;
-  XfDevBuf first, blk_counts, blk_offsets, send_counts, all_counts;
-  XfDevBuf send_keys, send_slot, pull_w, pull_v, grad_w, grad_v;      // worker side, bucketed by owner
+  XfWorkSet ws;
+  size_t set_bytes = 0;
+  XfDevBuf d_set, d_keys, d_w, d_v, d_gw, d_gv, grad_w, grad_v, bucket_cnt, all_counts;
   XfDevBuf recv_keys, recv_slots, resp_w, resp_v, rgrad_w, rgrad_v;   // owner side, grouped by source
   uint32_t* h_counts = nullptr;        // pinned S*S
   std::vector<uint64_t> send_off, recv_off, send_cnt, recv_cnt;
+  // XFLOW_MG_TRACE=1: CUDA events at the phase boundaries of every step, averages printed at destroy
+  bool trace = false;
+  std::vector<cudaEvent_t> tev;
+  double tsum[16] = {0};
+  uint64_t tsteps = 0;
 };
+static const char* kMgPhase[] = {"set clear + dedup", "counts allgather+sync", "a2a keys", "owner pull", "a2a values",
+                                 "(unused)", "fused step (work set)", "grads", "a2a grads", "owner updates"};
+#define XF_MG_TRACE_STEPS 512
+#define XF_MG_MARK(i) do { if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) cudaEventRecord(mg->tev[mg->tsteps * 11 + (i)], st); } while (0)
 
 int xf_mg_create(xf_trainer* tr) {
   xf_comm* c = tr->comm;
@@ -305,38 +259,53 @@ int xf_mg_create(xf_trainer* tr) {
     delete mg;
     return XF_ERR_ARG;
   }
-  mg->width = 0xFFFFFFFFFFFFFFFFull / (uint64_t)mg->S;
-  xf_table_config cfg = tr->table->cfg;
-  cfg.optimizer = XF_OPTIMIZER_SGD;  // layout with v and gv blocks only; no optimizer ever runs on the cache
-  cfg.v_init = XF_VINIT_ZERO;
-  cfg.capacity = 4ull * tr->cfg.max_nnz;  // load factor <= 0.25, never grows
-  cfg.shard_index = 0;
-  cfg.num_shards = 1;
-  int r = xf_table_create(&mg->wc, &cfg);
-  if (r != XF_OK) { delete mg; return r; }
-  const uint32_t nnz = tr->cfg.max_nnz;
-  mg->chunk = 4096;
-  mg->nblk = (nnz + mg->chunk - 1) / mg->chunk;
-  const size_t K = (size_t)tr->table->view.K;
   const int S = mg->S;
-  XF_TRY(mg->first.ensure((size_t)nnz * 4));
-  XF_TRY(mg->blk_counts.ensure((size_t)mg->nblk * S * 4));
-  XF_TRY(mg->blk_offsets.ensure((size_t)mg->nblk * S * 4));
-  XF_TRY(mg->send_counts.ensure((size_t)S * 4));
-  XF_TRY(mg->all_counts.ensure((size_t)S * S * 4));
-  XF_TRY(mg->send_keys.ensure((size_t)nnz * 8));
-  XF_TRY(mg->send_slot.ensure((size_t)nnz * 4));
-  XF_TRY(mg->pull_w.ensure((size_t)nnz * 4));
-  XF_TRY(mg->grad_w.ensure((size_t)nnz * 4));
+  mg->width = 0xFFFFFFFFFFFFFFFFull / (uint64_t)S;
+  const uint32_t nnz = tr->cfg.max_nnz;
+  const size_t K = (size_t)tr->table->view.K;
+  uint64_t cap_set = 1024;
+  while (cap_set < 2ull * nnz) cap_set <<= 1;  // load factor <= 0.5
+  uint32_t lg = 0;
+  while ((1ull << lg) < cap_set) ++lg;
+  mg->set_bytes = cap_set * 16;
+  const size_t tot = (size_t)S * nnz;  // bucket-major arrays, bucket stride = max_nnz
+  XF_TRY(mg->d_set.ensure(mg->set_bytes));
+  XF_TRY(mg->d_keys.ensure(tot * 8));
+  XF_TRY(mg->d_w.ensure(tot * 4));
+  XF_TRY(mg->d_gw.ensure(tot * 8));
+  XF_TRY(mg->grad_w.ensure(tot * 4));
   if (K) {
-    XF_TRY(mg->pull_v.ensure((size_t)nnz * 4 * K));
-    XF_TRY(mg->grad_v.ensure((size_t)nnz * 4 * K));
+    XF_TRY(mg->d_v.ensure(tot * 4 * K));
+    XF_TRY(mg->d_gv.ensure(tot * 4 * K));
+    XF_TRY(mg->grad_v.ensure(tot * 4 * K));
   }
+  XF_TRY(mg->bucket_cnt.ensure((size_t)S * 4));
+  XF_TRY(mg->all_counts.ensure((size_t)S * S * 4));
+  cudaStream_t st = tr->table->stream;
+  XF_CUDA_TRY(cudaMemsetAsync(mg->d_gw.p, 0, tot * 8, st));
+  if (K) XF_CUDA_TRY(cudaMemsetAsync(mg->d_gv.p, 0, tot * 4 * K, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  mg->ws.set = mg->d_set.as<uint8_t>();
+  mg->ws.mask = cap_set - 1;
+  mg->ws.log2cap = lg;
+  mg->ws.cap = nnz;
+  mg->ws.K = (int)K;
+  mg->ws.keys = mg->d_keys.as<uint64_t>();
+  mg->ws.w = mg->d_w.as<float>();
+  mg->ws.v = K ? mg->d_v.as<float>() : nullptr;
+  mg->ws.gw = mg->d_gw.as<double>();
+  mg->ws.gv = K ? mg->d_gv.as<float>() : nullptr;
   XF_CUDA_TRY(cudaHostAlloc(&mg->h_counts, (size_t)S * S * 4, cudaHostAllocDefault));
   mg->send_off.resize(S + 1);
   mg->recv_off.resize(S + 1);
   mg->send_cnt.resize(S);
   mg->recv_cnt.resize(S);
+  const char* tenv = getenv("XFLOW_MG_TRACE");
+  mg->trace = tenv && *tenv == '1';
+  if (mg->trace) {
+    mg->tev.resize(11 * XF_MG_TRACE_STEPS);
+    for (auto& e : mg->tev) cudaEventCreate(&e);
+  }
   tr->mg = mg;
   return XF_OK;
 }
@@ -344,20 +313,35 @@ int xf_mg_create(xf_trainer* tr) {
 void xf_mg_destroy(xf_trainer* tr) {
   XfMg* mg = (XfMg*)tr->mg;
   if (!mg) return;
-  XfDevBuf* bufs[] = {&mg->first, &mg->blk_counts, &mg->blk_offsets, &mg->send_counts, &mg->all_counts,
-                      &mg->send_keys, &mg->send_slot, &mg->pull_w, &mg->pull_v, &mg->grad_w, &mg->grad_v,
-                      &mg->recv_keys, &mg->recv_slots, &mg->resp_w, &mg->resp_v, &mg->rgrad_w, &mg->rgrad_v};
+  if (mg->trace && mg->tsteps) {
+    cudaDeviceSynchronize();
+    // skip the first steps (population / allocation); events were recorded without any extra sync
+    const uint64_t skip = mg->tsteps > 40 ? 30 : 0;
+    for (uint64_t t = skip; t < mg->tsteps; ++t)
+      for (int i = 0; i < 10; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, mg->tev[t * 11 + i], mg->tev[t * 11 + i + 1]);
+        mg->tsum[i] += ms;
+      }
+    const double n = (double)(mg->tsteps - skip);
+    fprintf(stderr, "[xflow mg trace] rank %d, steps %llu..%llu, mean ms per phase:\n", mg->rank,
+            (unsigned long long)skip, (unsigned long long)mg->tsteps);
+    double tot = 0;
+    for (int i = 0; i < 10; ++i) { fprintf(stderr, "    %-24s %8.4f\n", kMgPhase[i], mg->tsum[i] / n); tot += mg->tsum[i] / n; }
+    fprintf(stderr, "    %-24s %8.4f\n", "total", tot);
+  }
+  XfDevBuf* bufs[] = {&mg->d_set, &mg->d_keys, &mg->d_w, &mg->d_v, &mg->d_gw, &mg->d_gv, &mg->grad_w, &mg->grad_v,
+                      &mg->bucket_cnt, &mg->all_counts, &mg->recv_keys, &mg->recv_slots, &mg->resp_w, &mg->resp_v,
+                      &mg->rgrad_w, &mg->rgrad_v};
   for (XfDevBuf* b : bufs) b->release();
   if (mg->h_counts) cudaFreeHost(mg->h_counts);
-  xf_table_destroy(mg->wc);
+  for (auto& e : mg->tev) cudaEventDestroy(e);
   delete mg;
   tr->mg = nullptr;
 }
 
-int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm);
-
-// grouped all-to-all of `elem_bytes`-sized items: bucket q of `send` (send_off/cnt) goes to rank q,
-// segment q of `recv` (recv_off/cnt) comes from rank q.  scale = items per key (1 or K).
+// grouped all-to-all: bucket q of `send` (element offset soff[q], scnt[q] keys) goes to rank q, segment q
+// of `recv` comes from rank q.  `scale` = items of `elem_bytes` per key.
 static int xf_all_to_all(xf_comm* c, const void* send, const std::vector<uint64_t>& soff,
                          const std::vector<uint64_t>& scnt, void* recv, const std::vector<uint64_t>& roff,
                          const std::vector<uint64_t>& rcnt, size_t elem_bytes, size_t scale, cudaStream_t st) {
@@ -365,54 +349,54 @@ static int xf_all_to_all(xf_comm* c, const void* send, const std::vector<uint64_
   for (int q = 0; q < c->nranks; ++q) {
     if (scnt[q])
       XF_NCCL_TRY(g_nccl.Send((const char*)send + soff[q] * scale * elem_bytes, scnt[q] * scale * elem_bytes, ncclChar, q,
-                           c->nccl, st));
+                              c->nccl, st));
     if (rcnt[q])
       XF_NCCL_TRY(g_nccl.Recv((char*)recv + roff[q] * scale * elem_bytes, rcnt[q] * scale * elem_bytes, ncclChar, q,
-                           c->nccl, st));
+                              c->nccl, st));
   }
   XF_NCCL_TRY(g_nccl.GroupEnd());
   return XF_OK;
 }
 
 int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys, const uint8_t* d_labels,
-               uint32_t rows, uint32_t nnz, int mode, float* d_abs) {
+               uint32_t rows, uint32_t nnz, int mode, float* d_abs, cudaEvent_t* pm) {
   XfMg* mg = (XfMg*)tr->mg;
   xf_comm* c = tr->comm;
   xf_table* t = tr->table;
   cudaStream_t st = t->stream;
   const int S = mg->S;
   const size_t K = (size_t)t->view.K;
-  const XfTableView wc = mg->wc->view;
-  const uint32_t nblk = (nnz + mg->chunk - 1) / mg->chunk;
+  const XfWorkSet& ws = mg->ws;
 
-  // ---- worker: dedup + bucket by owner
+  // ---- worker: clear the set (one streaming memset), dedup + number + bucket by owner
+  XF_MG_MARK(0);
+  XF_CUDA_TRY(cudaMemsetAsync(mg->d_set.p, 0xFF, mg->set_bytes, st));
+  XF_CUDA_TRY(cudaMemsetAsync(mg->bucket_cnt.p, 0, (size_t)S * 4, st));
   if (nnz) {
-    xf_k_mg_dedup<<<nblk, XF_MG_BLOCK, 0, st>>>(wc, d_keys, nnz, mg->chunk, mg->width, S, mg->first.as<uint32_t>(),
-                                                 mg->blk_counts.as<uint32_t>());
-    xf_k_mg_scan<<<1, 32, 0, st>>>(mg->blk_counts.as<uint32_t>(), nblk, S, mg->blk_offsets.as<uint32_t>(),
-                                   mg->send_counts.as<uint32_t>());
-    xf_k_mg_scatter<<<nblk, XF_MG_BLOCK, 0, st>>>(d_keys, mg->first.as<uint32_t>(), nnz, mg->chunk, mg->width, S,
-                                                   mg->blk_offsets.as<uint32_t>(), mg->send_keys.as<uint64_t>(),
-                                                   mg->send_slot.as<uint32_t>());
-    tr->launches += 3;
-  } else {
-    XF_CUDA_TRY(cudaMemsetAsync(mg->send_counts.p, 0, (size_t)S * 4, st));
+    const uint32_t per_block = XF_WS_BLOCK * XF_WS_TOK;
+    xf_k_ws_dedup<<<(nnz + per_block - 1) / per_block, XF_WS_BLOCK, 0, st>>>(ws, d_keys, nnz, mg->width, S,
+                                                                              mg->bucket_cnt.as<uint32_t>());
+    ++tr->launches;
   }
   // ---- bucket sizes of every rank (the only host sync of the step)
-  XF_NCCL_TRY(g_nccl.AllGather(mg->send_counts.p, mg->all_counts.p, (size_t)S, ncclUint32, c->nccl, st));
+  XF_MG_MARK(1);
+  XF_NCCL_TRY(g_nccl.AllGather(mg->bucket_cnt.p, mg->all_counts.p, (size_t)S, ncclUint32, c->nccl, st));
   XF_CUDA_TRY(cudaMemcpyAsync(mg->h_counts, mg->all_counts.p, (size_t)S * S * 4, cudaMemcpyDeviceToHost, st));
   XF_CUDA_TRY(cudaStreamSynchronize(st));
   uint64_t n_send = 0, n_recv = 0;
+  XfBucketCounts bc;
+  memset(&bc, 0, sizeof(bc));
+  uint32_t max_bucket = 0;
   for (int q = 0; q < S; ++q) {
     mg->send_cnt[q] = mg->h_counts[mg->rank * S + q];   // my keys owned by q
     mg->recv_cnt[q] = mg->h_counts[q * S + mg->rank];   // q's keys owned by me
-    mg->send_off[q] = n_send;
+    mg->send_off[q] = (uint64_t)q * ws.cap;             // bucket-major work-set arrays
     mg->recv_off[q] = n_recv;
+    bc.c[q] = (uint32_t)mg->send_cnt[q];
+    if (bc.c[q] > max_bucket) max_bucket = bc.c[q];
     n_send += mg->send_cnt[q];
     n_recv += mg->recv_cnt[q];
   }
-  mg->send_off[S] = n_send;
-  mg->recv_off[S] = n_recv;
   XF_TRY(mg->recv_keys.ensure(n_recv * 8 + 8));
   XF_TRY(mg->recv_slots.ensure(n_recv * 4 + 4));
   XF_TRY(mg->resp_w.ensure(n_recv * 4 + 4));
@@ -423,9 +407,10 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
   }
 
   // ---- all-to-all #1: keys to their owners (the Pull request, kv_app.h:147-165)
-  XF_TRY(xf_all_to_all(c, mg->send_keys.p, mg->send_off, mg->send_cnt, mg->recv_keys.p, mg->recv_off, mg->recv_cnt,
-                       8, 1, st));
+  XF_MG_MARK(2);
+  XF_TRY(xf_all_to_all(c, ws.keys, mg->send_off, mg->send_cnt, mg->recv_keys.p, mg->recv_off, mg->recv_cnt, 8, 1, st));
   // ---- owner: Pull handler on this shard (insert-on-pull, ftrl.h:56,114-120)
+  XF_MG_MARK(3);
   if (n_recv) {
     XF_TRY(t->ensure_room(n_recv));
     xf_launch_probe(t->view, mg->recv_keys.as<uint64_t>(), n_recv, true, mg->recv_slots.as<uint32_t>(),
@@ -437,45 +422,51 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
       ++tr->launches;
     }
   }
-  // ---- all-to-all #2: values back (the Pull response)
-  XF_TRY(xf_all_to_all(c, mg->resp_w.p, mg->recv_off, mg->recv_cnt, mg->pull_w.p, mg->send_off, mg->send_cnt, 4, 1, st));
-  if (K)
-    XF_TRY(xf_all_to_all(c, mg->resp_v.p, mg->recv_off, mg->recv_cnt, mg->pull_v.p, mg->send_off, mg->send_cnt, 4, K, st));
+  // ---- all-to-all #2: values back, straight into the work set (the Pull response)
+  XF_MG_MARK(4);
+  XF_TRY(xf_all_to_all(c, mg->resp_w.p, mg->recv_off, mg->recv_cnt, ws.w, mg->send_off, mg->send_cnt, 4, 1, st));
+  if (K) XF_TRY(xf_all_to_all(c, mg->resp_v.p, mg->recv_off, mg->recv_cnt, ws.v, mg->send_off, mg->send_cnt, 4, K, st));
 
-  // ---- worker: forward / residual / gradient accumulation on the cache table, same kernel as S = 1
-  if (n_send) {
-    xf_k_mg_fill<<<xf_grid_for(n_send * (K + 1), 256, 8), 256, 0, st>>>(wc, mg->send_slot.as<uint32_t>(),
-                                                                         (uint32_t)n_send, mg->pull_w.as<float>(),
-                                                                         K ? mg->pull_v.as<float>() : nullptr);
-    ++tr->launches;
-  }
-  xf_launch_step(wc, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
-                 (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
-                 mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
+  // ---- worker: forward / residual / gradient accumulation against the work set
+  XF_MG_MARK(5);
+  XF_MG_MARK(6);
+  if (pm) XF_CUDA_TRY(cudaEventRecord(pm[0], st));
+  xf_launch_step_ws(ws, d_row_ptr, d_keys, d_labels, (int)rows, mode,
+                    (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
+                    mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
+  if (pm) XF_CUDA_TRY(cudaEventRecord(pm[1], st));
   ++tr->launches;
-  if (n_send) {
-    xf_k_mg_grads<<<xf_grid_for(n_send * (K + 1), 256, 8), 256, 0, st>>>(
-        wc, mg->send_slot.as<uint32_t>(), (uint32_t)n_send, (double)rows, mode == 0 ? 1 : 0, mg->grad_w.as<float>(),
-        K ? mg->grad_v.as<float>() : nullptr);
-    xf_k_mg_clear<<<xf_grid_for(n_send, 256, 8), 256, 0, st>>>(wc, mg->send_slot.as<uint32_t>(), (uint32_t)n_send);
-    tr->launches += 2;
-  }
+  XF_MG_MARK(7);
   if (mode != 0) {
     XF_CUDA_TRY(cudaGetLastError());
-    return XF_OK;
+    return XF_OK;  // forward only: nothing was accumulated
+  }
+  if (n_send) {
+    dim3 grid((unsigned)xf_grid_for((uint64_t)max_bucket * (K + 1), 256, 4), (unsigned)S);
+    xf_k_ws_grads<<<grid, 256, 0, st>>>(ws, bc, (double)rows, 1, mg->grad_w.as<float>(),
+                                        K ? mg->grad_v.as<float>() : nullptr);
+    ++tr->launches;
   }
 
   // ---- all-to-all #3: gradients to the owners (the Push, kv_app.h:110-118)
+  XF_MG_MARK(8);
   XF_TRY(xf_all_to_all(c, mg->grad_w.p, mg->send_off, mg->send_cnt, mg->rgrad_w.p, mg->recv_off, mg->recv_cnt, 4, 1, st));
   if (K)
     XF_TRY(xf_all_to_all(c, mg->grad_v.p, mg->send_off, mg->send_cnt, mg->rgrad_v.p, mg->recv_off, mg->recv_cnt, 4, K, st));
   // ---- owner: Push handler, one optimizer step per (source, key), sources in rank order
+  XF_MG_MARK(9);
+  if (pm) XF_CUDA_TRY(cudaEventRecord(pm[2], st));
   for (int q = 0; q < S; ++q) {
     if (!mg->recv_cnt[q]) continue;
     const uint64_t off = mg->recv_off[q];
     xf_launch_update_pushed(t->view, mg->recv_slots.as<uint32_t>() + off, mg->recv_cnt[q],
                             mg->rgrad_w.as<float>() + off, K ? mg->rgrad_v.as<float>() + off * K : nullptr, st);
     ++tr->launches;
+  }
+  if (pm) XF_CUDA_TRY(cudaEventRecord(pm[3], st));
+  if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) {
+    cudaEventRecord(mg->tev[mg->tsteps * 11 + 10], st);
+    ++mg->tsteps;
   }
   tr->host_unique += n_send;  // statistics: unique keys of this rank's batch
   XF_CUDA_TRY(cudaGetLastError());

@@ -92,7 +92,7 @@ struct xf_trainer {
   void* mg = nullptr;                   // multi-GPU exchange state (comm.cu)
   // optional per-kernel timing (xf_trainer_set_profile): events around the kernels of each step
   bool profile = false;
-  std::vector<cudaEvent_t> prof_events;  // XF_PROF_MARKS per step
+  std::vector<cudaEvent_t> prof_events;  // 4 marks per step: step kernel [0,1], optimizer kernel(s) [2,3]
   size_t prof_used = 0;
 };
 
@@ -100,6 +100,6 @@ struct xf_trainer {
 int xf_mg_create(xf_trainer* tr);
 void xf_mg_destroy(xf_trainer* tr);
 int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys, const uint8_t* d_labels,
-               uint32_t rows, uint32_t nnz, int mode, float* d_abs_loss);
+               uint32_t rows, uint32_t nnz, int mode, float* d_abs_loss, cudaEvent_t* prof_marks);
 int xf_comm_nranks(xf_comm* c);
 int xf_comm_rank(xf_comm* c);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "table.cuh"
+#include "workset.cuh"
 
 int xf_vec_for(int K);
 int xf_tps_for(int K);
@@ -28,3 +29,6 @@ void xf_launch_export(const XfTableView& t, const uint32_t* slots, const uint64_
 void xf_launch_rehash(const XfTableView& src, const XfTableView& dst, cudaStream_t st);
 void xf_launch_list_keys(const XfTableView& t, uint64_t* keys_out, unsigned long long* count, uint64_t max_out,
                          cudaStream_t st);
+void xf_launch_step_ws(const XfWorkSet& ws, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* labels,
+                       int B, int mode, float* loss_out, float* pctr_out, float* abs_loss_sum, cudaStream_t st);
+int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm);
