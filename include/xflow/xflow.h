@@ -30,21 +30,23 @@
 
 #include "../xflow_b200.h"
 
+#define XF_CXX_API __attribute__((visibility("default")))
+
 namespace xflow {
 
 // global hyper-parameters, same names and defaults as the reference
-extern int w_dim;            // ftrl.h:15
-extern int v_dim;            // ftrl.h:16  (10)
-extern float alpha;          // ftrl.h:17  (5e-2)
-extern float beta;           // ftrl.h:18  (1.0)
-extern float lambda1;        // ftrl.h:19  (5e-5)
-extern float lambda2;        // ftrl.h:20  (10.0)
-extern float learning_rate;  // sgd.h:16   (1e-3)
+extern XF_CXX_API int w_dim;            // ftrl.h:15
+extern XF_CXX_API int v_dim;            // ftrl.h:16  (10)
+extern XF_CXX_API float alpha;          // ftrl.h:17  (5e-2)
+extern XF_CXX_API float beta;           // ftrl.h:18  (1.0)
+extern XF_CXX_API float lambda1;        // ftrl.h:19  (5e-5)
+extern XF_CXX_API float lambda2;        // ftrl.h:20  (10.0)
+extern XF_CXX_API float learning_rate;  // sgd.h:16   (1e-3)
 
 enum class Optimizer { FTRL = 0, SGD = 1 };
 
 // Owns the device-resident parameter table(s) of this process (one shard per GPU).
-class Server {
+class XF_CXX_API Server {
  public:
   // latent_dim < 0: size the table for FM with xflow::v_dim (the reference server always
   // installs both the w and the v handle, server.h:23-28)
@@ -70,7 +72,7 @@ struct auc_key {  // Base::auc_key base.h:79-82
   float pctr;
 };
 
-class WorkerBase {
+class XF_CXX_API WorkerBase {
  public:
   virtual ~WorkerBase();
   void train();                              // lr_worker.cc:207-217 / fm_worker.cc:277-287
@@ -110,18 +112,18 @@ class WorkerBase {
   std::ofstream md;
 };
 
-class LRWorker : public WorkerBase {
+class XF_CXX_API LRWorker : public WorkerBase {
  public:
   LRWorker(const char* train_file, const char* test_file);
 };
 
-class FMWorker : public WorkerBase {
+class XF_CXX_API FMWorker : public WorkerBase {
  public:
   FMWorker(const char* train_file, const char* test_file);
 };
 
 // what a ps-lite process would ask its environment (ps.h): single-box, one process per GPU
-int MyRank();
+XF_CXX_API int MyRank();
 
 }  // namespace xflow
 

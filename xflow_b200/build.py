@@ -64,6 +64,14 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    # the reference's CLI (src/model/main.cc) on top of the library
+    bindir = os.path.join(ROOT, "xflow_b200", "bin")
+    os.makedirs(bindir, exist_ok=True)
+    exe = os.path.join(bindir, "xflow_lr")
+    main_cc = os.path.join(CSRC, "main.cc")
+    if force or _newer(main_cc, exe) or _newer(LIB, exe):
+        subprocess.check_call([os.environ.get("CXX_HOST", "g++"), "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                               main_cc, "-o", exe, "-L" + LIBDIR, "-lxflow_b200", "-Wl,-rpath," + LIBDIR])
     return LIB
 
 
