@@ -324,8 +324,12 @@ def main():
         b_step, b_update = algorithmic_bytes(wl, B, nnz, U)
         t_step = prof["step_ms"] / max(prof["steps"], 1) * 1e-3
         t_upd = prof["update_ms"] / max(prof["steps"], 1) * 1e-3
-        kern = [("xf_k_step (fused pull+forward+gradient)", b_step, t_step),
-                ("xf_k_update (FTRL over touched rows)", b_update, t_upd)]
+        if t_upd > 0:
+            kern = [("xf_k_step (fused pull+forward+gradient)", b_step, t_step),
+                    ("xf_k_update (FTRL over touched rows)", b_update, t_upd)]
+        else:
+            # LR tables fold the optimizer step into the next touch of a row: one kernel does all of it
+            kern = [("xf_k_step_lr_lazy (pull+forward+gradient+optimizer in one kernel)", b_step + b_update, t_step)]
         dom = max(kern, key=lambda k: k[2])
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")

@@ -124,7 +124,11 @@ def test_random_batches_match_oracle(model, opt, K, dist):
                 assert_close(ge[k], oe[k], "%s step %d" % (k, step))
         else:
             for k in ("w", "nw", "zw") + (("v", "nv", "zv") if K else ()):
-                assert_close_noise_aware(ge[k], oe[k], xe[k], "%s step %d" % (k, step), max_noisy_frac=0.02)
+                # the latent-gradient accumulators are f32 vector REDs (one L2 transaction per 16 B): on
+                # keys with thousands of occurrences per batch their own order noise reaches ~1e-5, on
+                # top of the reference's; the scalar accumulator is f64 and exact
+                rel = 1e-4 if k in ("v", "nv", "zv") else 1e-5
+                assert_close_noise_aware(ge[k], oe[k], xe[k], "%s step %d" % (k, step), rel=rel, max_noisy_frac=0.02)
         assert tr.stats()["unique_keys"] >= U
     st = tr.stats()
     assert st["steps"] == 4 and st["rows"] == 4 * B

@@ -3,6 +3,7 @@
 // kernels in kernels.cu.  There is no CPU fallback anywhere in this file.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -114,6 +115,10 @@ int xf_table::check_error() {
   int e = 0;
   XF_CUDA_TRY(cudaMemcpyAsync(&e, d_error, sizeof(int), cudaMemcpyDeviceToHost, stream));
   XF_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (e == 2) {
+    xf_set_error("internal error: a row was never opened for the batch (lazy-update protocol)");
+    return XF_ERR_STATE;
+  }
   if (e) {
     xf_set_error("table probe sequence overflowed (table full)");
     return XF_ERR_FULL;
@@ -129,6 +134,23 @@ int xf_table::grow(uint64_t new_capacity) {
   ++launches;
   XF_CUDA_TRY(cudaStreamSynchronize(stream));
   XF_CUDA_TRY(cudaFree(old.base));
+  return XF_OK;
+}
+
+int xf_table::next_seq() {
+  if ((size_t)seq + 2 >= rows_cap) {
+    const size_t ncap = rows_cap * 2;
+    uint32_t* nbuf = nullptr;
+    XF_CUDA_TRY(cudaMalloc(&nbuf, ncap * sizeof(uint32_t)));
+    XF_CUDA_TRY(cudaMemsetAsync(nbuf, 0, ncap * sizeof(uint32_t), stream));
+    XF_CUDA_TRY(cudaMemcpyAsync(nbuf, d_rows_by_seq, rows_cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+    XF_CUDA_TRY(cudaStreamSynchronize(stream));
+    XF_CUDA_TRY(cudaFree(d_rows_by_seq));
+    d_rows_by_seq = nbuf;
+    rows_cap = ncap;
+    view.rows_by_seq = nbuf;
+  }
+  ++seq;
   return XF_OK;
 }
 
@@ -178,6 +200,17 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
   else v.v_init = (v.opt == XF_OPT_FTRL) ? XF_INIT_COUNTER : XF_INIT_DEFAULT;
   v.size = t->d_size;
   v.error = t->d_error;
+  // K == 0 (LR) tables fold the optimizer step into the next touch of a row (step.cu); K > 0 tables
+  // keep the separate optimizer kernel.  XFLOW_EAGER=1 forces the two-kernel path (A/B measurements).
+  const char* eager = getenv("XFLOW_EAGER");
+  v.lazy = (v.K == 0 && !(eager && *eager == '1')) ? 1 : 0;
+  v.rows_by_seq = nullptr;
+  if (v.lazy) {
+    t->rows_cap = 1u << 16;
+    XF_CUDA_TRY(cudaMalloc(&t->d_rows_by_seq, t->rows_cap * sizeof(uint32_t)));
+    XF_CUDA_TRY(cudaMemsetAsync(t->d_rows_by_seq, 0, t->rows_cap * sizeof(uint32_t), t->stream));
+    v.rows_by_seq = t->d_rows_by_seq;
+  }
   int r = t->alloc_table(cfg->capacity ? cfg->capacity : (1ull << 20));
   if (r != XF_OK) { delete t; return r; }
   XF_CUDA_TRY(cudaStreamSynchronize(t->stream));
@@ -193,6 +226,7 @@ XF_DLL int xf_table_destroy(xf_table* t) {
   if (t->view.base) cudaFree(t->view.base);
   cudaFree(t->d_size);
   cudaFree(t->d_error);
+  if (t->d_rows_by_seq) cudaFree(t->d_rows_by_seq);
   t->s_keys.release(); t->s_slots.release(); t->s_w.release(); t->s_v.release();
   t->s_nw.release(); t->s_zw.release(); t->s_nv.release(); t->s_zv.release(); t->s_present.release();
   if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
@@ -558,6 +592,21 @@ static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const 
     tr->prof_used += 4;
     if (tr->mg) return xf_mg_step(tr, d_row_ptr, d_keys, d_labels, rows, nnz, mode, d_abs, pe);
     XF_CUDA_TRY(cudaEventRecord(pe[0], st));
+  }
+  if (t->view.lazy) {
+    // one kernel: the optimizer step of earlier batches is folded in as rows are touched
+    if (mode == 0) XF_TRY(t->next_seq());
+    xf_launch_step_lr_lazy(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, t->seq, t->d_rows_by_seq,
+                           (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
+                           mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, tr->d_unique_total, st);
+    ++tr->launches;
+    if (prof) {
+      XF_CUDA_TRY(cudaEventRecord(pe[1], st));
+      XF_CUDA_TRY(cudaEventRecord(pe[2], st));
+      XF_CUDA_TRY(cudaEventRecord(pe[3], st));
+    }
+    XF_CUDA_TRY(cudaGetLastError());
+    return XF_OK;
   }
   xf_launch_step(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
                  (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,

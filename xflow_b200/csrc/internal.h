@@ -56,6 +56,11 @@ struct xf_table {
   uint64_t size_bound = 0;   // host-side upper bound on the number of live keys
   uint64_t launches = 0;
   int refs = 1;              // the creator + every trainer bound to the table (destroy order is free)
+  // lazy ("update on next touch") tables: batch sequence number and the per-batch row counts
+  uint32_t seq = 0;
+  uint32_t* d_rows_by_seq = nullptr;
+  size_t rows_cap = 0;
+  int next_seq();            // advances seq, growing rows_by_seq when needed
   // scratch for the host-pointer API
   XfDevBuf s_keys, s_slots, s_w, s_v, s_nw, s_zw, s_nv, s_zv, s_present;
 

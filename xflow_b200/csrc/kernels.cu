@@ -129,6 +129,7 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
     if (rowp == nullptr) continue;
 
     if (q == 0) {
+      if (!SLOTG) xf_apply_pending(t, h);  // lazy tables: fold the pending batch step in first
       if (part & 1) {
         // the accumulated sum is rounded to float once (push_gradient is a float vector), then / rows
         const float g = SLOTG ? xf_div_rows((float)h.g, rows) : gw[i];
@@ -206,7 +207,10 @@ __global__ void xf_k_probe(XfTableView t, const uint64_t* __restrict__ keys, uin
     h.w = 0.f;
     int64_t s = xf_probe<INSERT>(t, keys[i], &h);
     slots[i] = s >= 0 ? (uint32_t)s : 0xFFFFFFFFu;
-    if (w_out) w_out[i] = s >= 0 ? h.w : 0.f;
+    if (w_out) {
+      if (s >= 0) xf_apply_pending(t, h);  // lazy tables: the value the reference's server would hold
+      w_out[i] = s >= 0 ? h.w : 0.f;
+    }
   }
 }
 
@@ -250,6 +254,7 @@ __global__ void xf_k_import(XfTableView t, const uint32_t* __restrict__ slots, u
         *reinterpret_cast<float2*>(rowp + 8) = make_float2(w[i], nw ? nw[i] : 0.f);
         *reinterpret_cast<float*>(rowp + 16) = zw ? zw[i] : 0.f;
         *reinterpret_cast<unsigned long long*>(rowp + 24) = XF_NEG_ZERO_BITS64;
+        if (t.lazy) *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = 0u;  // no pending step
       }
       if (v && K > 0) *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = XF_FLAG_V_READY;
     } else if (v) {
@@ -281,7 +286,10 @@ __global__ void xf_k_export(XfTableView t, const uint32_t* __restrict__ slots, c
     if (c == 0) {
       XfHead h;
       h.w = h.n = h.z = 0.f;
-      if (have) h = xf_load_head(rowp);
+      if (have) {
+        h = xf_load_head(rowp);
+        xf_apply_pending(t, h);
+      }
       if (present) present[i] = have ? 1 : 0;
       if (w) w[i] = h.w;
       if (nw) nw[i] = h.n;

@@ -32,3 +32,7 @@ void xf_launch_list_keys(const XfTableView& t, uint64_t* keys_out, unsigned long
 void xf_launch_step_ws(const XfWorkSet& ws, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* labels,
                        int B, int mode, float* loss_out, float* pctr_out, float* abs_loss_sum, cudaStream_t st);
 int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm);
+void xf_launch_step_lr_lazy(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys,
+                            const uint8_t* labels, int B, int mode, uint32_t seq, uint32_t* rows_by_seq,
+                            float* loss_out, float* pctr_out, float* abs_loss_sum, unsigned long long* unique_total,
+                            cudaStream_t st);

@@ -372,3 +372,4 @@ void xf_launch_step_ws(const XfWorkSet& ws, const uint32_t* row_ptr, const uint6
   }
 #undef XF_WS_ARGS
 }
+

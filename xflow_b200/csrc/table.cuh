@@ -53,7 +53,14 @@ struct XfTableView {
   float alpha, beta, lambda1, lambda2, learning_rate;
   unsigned long long* size;   // number of keys present
   int* error;                 // set to 1 when a probe sequence overflows (table full)
+  // "update on next touch" (K == 0 tables, see step.cu): the flags word of a row is then a TAG =
+  // sequence number of the batch whose residual sum sits in g (0: nothing pending, XF_TAG_LOCKED: a
+  // thread is folding the pending step into the row right now); rows_by_seq[tag] is that batch's row
+  // count (the divisor of lr_worker.cc:116-118).  Every reader applies a pending step on the fly.
+  int lazy;
+  const uint32_t* rows_by_seq;
 };
+#define XF_TAG_LOCKED 0xFFFFFFFFu
 
 __host__ __device__ inline uint32_t xf_row_stride(int K, int opt) {
   uint32_t nblk = (opt == XF_OPT_FTRL) ? 4u : 2u;
@@ -184,7 +191,9 @@ __device__ __forceinline__ int64_t xf_probe(const XfTableView& t, uint64_t key, 
 __device__ __forceinline__ float xf_sigmoid(float x) {
   if (x < -30.f) return (float)1e-6;
   if (x > 30.f) return 1.0f;
-  double ex = pow(2.718281828, (double)x);
+  // pow(2.718281828, x) as exp(x * ln 2.718281828) in double: same value to ~3e-15 relative (far below
+  // the final float rounding), a third of the registers and instructions of the generic double pow
+  const double ex = exp((double)x * 0.9999999998311266);
   return (float)(ex / (1.0 + ex));
 }
 
@@ -218,6 +227,21 @@ __device__ __forceinline__ void xf_opt_coord(const XfTableView& t, float g, floa
 
 // push_gradient[i] /= 1.0 * loss.size()  lr_worker.cc:116-118 ; fm_worker.cc:150-156 (double divide)
 __device__ __forceinline__ float xf_div_rows(float g, double rows) { return (float)((double)g / rows); }
+
+// Lazy tables: the row as the reference's server would hold it — i.e. with the pending optimizer step
+// (the Push of the batch named by the tag) applied.  Pure function of the snapshot; writes nothing.
+__device__ __forceinline__ bool xf_has_pending(const XfTableView& t, const XfHead& h) {
+  return t.lazy && h.flags != 0u && h.flags != XF_TAG_LOCKED;
+}
+__device__ __forceinline__ void xf_apply_pending(const XfTableView& t, XfHead& h) {
+  if (!xf_has_pending(t, h)) return;
+  const double rows = (double)__ldg(t.rows_by_seq + h.flags);
+  // the residual sum is rounded to float once (push_gradient is a float vector), then divided
+  const float g = xf_div_rows((float)h.g, rows);
+  xf_opt_coord(t, g, h.w, h.n, h.z);
+  h.flags = 0u;
+  h.g = 0.0;
+}
 
 __device__ __forceinline__ float xf_warp_sum(float v) {
 #pragma unroll
