@@ -675,6 +675,7 @@ static int xf_upload_batch(xf_trainer* tr, XfBatchBuf& b, const uint32_t* row_pt
   XF_CUDA_TRY(cudaEventRecord(b.staged, tr->copy_stream));
   XF_CUDA_TRY(cudaEventRecord(b.copied, tr->copy_stream));
   XF_CUDA_TRY(cudaStreamWaitEvent(tr->table->stream, b.copied, 0));
+  tr->input_ready = b.copied;  // the sharded path starts its dedup on another stream
   return XF_OK;
 }
 

@@ -45,6 +45,7 @@ struct XfNccl {
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclCommSplit) CommSplit = nullptr;  // optional (NCCL >= 2.18)
   bool ok = false;
 };
 static XfNccl g_nccl;
@@ -67,6 +68,7 @@ static int xf_nccl_bind() {
   XF_BIND(GetUniqueId) XF_BIND(CommInitRank) XF_BIND(CommDestroy) XF_BIND(AllReduce) XF_BIND(AllGather)
   XF_BIND(Send) XF_BIND(Recv) XF_BIND(GroupStart) XF_BIND(GroupEnd) XF_BIND(GetErrorString)
 #undef XF_BIND
+  g_nccl.CommSplit = reinterpret_cast<decltype(g_nccl.CommSplit)>(dlsym(h, "ncclCommSplit"));
   g_nccl.ok = true;
   return XF_OK;
 }
@@ -82,6 +84,7 @@ static int xf_nccl_bind() {
 
 struct xf_comm {
   ncclComm_t nccl = nullptr;
+  ncclComm_t nccl2 = nullptr;  // same ranks, independent resources: bucket-size allgather of the NEXT batch
   int rank = 0, nranks = 1, device = 0;
 };
 
@@ -113,12 +116,16 @@ XF_DLL int xf_comm_create(xf_comm** out, const uint8_t id[XF_COMM_ID_BYTES], int
     delete c;
     return XF_ERR_COMM;
   }
+  if (g_nccl.CommSplit && nranks > 1) {
+    if (g_nccl.CommSplit(c->nccl, 0, rank, &c->nccl2, nullptr) != ncclSuccess) c->nccl2 = nullptr;
+  }
   *out = c;
   return XF_OK;
 }
 
 XF_DLL int xf_comm_destroy(xf_comm* c) {
   if (!c) return XF_OK;
+  if (c->nccl2) g_nccl.CommDestroy(c->nccl2);
   if (c->nccl) g_nccl.CommDestroy(c->nccl);
   delete c;
   return XF_OK;
@@ -232,9 +239,14 @@ __global__ void xf_k_ws_grads(XfWorkSet ws, XfBucketCounts cnt, double rows, int
 struct XfMg {
   int S = 1, rank = 0;
   uint64_t width = 0;
-  XfWorkSet ws;
+  // Two work sets: batch b+1 is deduplicated (second stream, second communicator for its bucket-size
+  // allgather) while batch b's gradients travel and its owner updates run on the table stream.
+  XfWorkSet ws2[2];
   size_t set_bytes = 0;
-  XfDevBuf d_set, d_keys, d_w, d_v, d_gw, d_gv, grad_w, grad_v, bucket_cnt, all_counts;
+  XfDevBuf d_set[2], d_keys[2], d_w[2], d_v[2], d_gw[2], d_gv[2], grad_w[2], grad_v[2], bucket_cnt[2], all_counts;
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_free[2] = {nullptr, nullptr};  // work set no longer read by the table stream
+  uint64_t step_no = 0;
   XfDevBuf recv_keys, recv_slots, resp_w, resp_v, rgrad_w, rgrad_v;   // owner side, grouped by source
   uint32_t* h_counts = nullptr;        // pinned S*S
   std::vector<uint64_t> send_off, recv_off, send_cnt, recv_cnt;
@@ -269,32 +281,37 @@ int xf_mg_create(xf_trainer* tr) {
   while ((1ull << lg) < cap_set) ++lg;
   mg->set_bytes = cap_set * 16;
   const size_t tot = (size_t)S * nnz;  // bucket-major arrays, bucket stride = max_nnz
-  XF_TRY(mg->d_set.ensure(mg->set_bytes));
-  XF_TRY(mg->d_keys.ensure(tot * 8));
-  XF_TRY(mg->d_w.ensure(tot * 4));
-  XF_TRY(mg->d_gw.ensure(tot * 8));
-  XF_TRY(mg->grad_w.ensure(tot * 4));
-  if (K) {
-    XF_TRY(mg->d_v.ensure(tot * 4 * K));
-    XF_TRY(mg->d_gv.ensure(tot * 4 * K));
-    XF_TRY(mg->grad_v.ensure(tot * 4 * K));
-  }
-  XF_TRY(mg->bucket_cnt.ensure((size_t)S * 4));
-  XF_TRY(mg->all_counts.ensure((size_t)S * S * 4));
   cudaStream_t st = tr->table->stream;
-  XF_CUDA_TRY(cudaMemsetAsync(mg->d_gw.p, 0, tot * 8, st));
-  if (K) XF_CUDA_TRY(cudaMemsetAsync(mg->d_gv.p, 0, tot * 4 * K, st));
+  XF_CUDA_TRY(cudaStreamCreateWithFlags(&mg->st2, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    XF_TRY(mg->d_set[b].ensure(mg->set_bytes));
+    XF_TRY(mg->d_keys[b].ensure(tot * 8));
+    XF_TRY(mg->d_w[b].ensure(tot * 4));
+    XF_TRY(mg->d_gw[b].ensure(tot * 8));
+    XF_TRY(mg->grad_w[b].ensure(tot * 4));
+    if (K) {
+      XF_TRY(mg->d_v[b].ensure(tot * 4 * K));
+      XF_TRY(mg->d_gv[b].ensure(tot * 4 * K));
+      XF_TRY(mg->grad_v[b].ensure(tot * 4 * K));
+    }
+    XF_TRY(mg->bucket_cnt[b].ensure((size_t)S * 4));
+    XF_CUDA_TRY(cudaMemsetAsync(mg->d_gw[b].p, 0, tot * 8, st));
+    if (K) XF_CUDA_TRY(cudaMemsetAsync(mg->d_gv[b].p, 0, tot * 4 * K, st));
+    XF_CUDA_TRY(cudaEventCreateWithFlags(&mg->ev_free[b], cudaEventDisableTiming));
+    XfWorkSet& w = mg->ws2[b];
+    w.set = mg->d_set[b].as<uint8_t>();
+    w.mask = cap_set - 1;
+    w.log2cap = lg;
+    w.cap = nnz;
+    w.K = (int)K;
+    w.keys = mg->d_keys[b].as<uint64_t>();
+    w.w = mg->d_w[b].as<float>();
+    w.v = K ? mg->d_v[b].as<float>() : nullptr;
+    w.gw = mg->d_gw[b].as<double>();
+    w.gv = K ? mg->d_gv[b].as<float>() : nullptr;
+  }
+  XF_TRY(mg->all_counts.ensure((size_t)S * S * 4));
   XF_CUDA_TRY(cudaStreamSynchronize(st));
-  mg->ws.set = mg->d_set.as<uint8_t>();
-  mg->ws.mask = cap_set - 1;
-  mg->ws.log2cap = lg;
-  mg->ws.cap = nnz;
-  mg->ws.K = (int)K;
-  mg->ws.keys = mg->d_keys.as<uint64_t>();
-  mg->ws.w = mg->d_w.as<float>();
-  mg->ws.v = K ? mg->d_v.as<float>() : nullptr;
-  mg->ws.gw = mg->d_gw.as<double>();
-  mg->ws.gv = K ? mg->d_gv.as<float>() : nullptr;
   XF_CUDA_TRY(cudaHostAlloc(&mg->h_counts, (size_t)S * S * 4, cudaHostAllocDefault));
   mg->send_off.resize(S + 1);
   mg->recv_off.resize(S + 1);
@@ -330,10 +347,16 @@ void xf_mg_destroy(xf_trainer* tr) {
     for (int i = 0; i < 10; ++i) { fprintf(stderr, "    %-24s %8.4f\n", kMgPhase[i], mg->tsum[i] / n); tot += mg->tsum[i] / n; }
     fprintf(stderr, "    %-24s %8.4f\n", "total", tot);
   }
-  XfDevBuf* bufs[] = {&mg->d_set, &mg->d_keys, &mg->d_w, &mg->d_v, &mg->d_gw, &mg->d_gv, &mg->grad_w, &mg->grad_v,
-                      &mg->bucket_cnt, &mg->all_counts, &mg->recv_keys, &mg->recv_slots, &mg->resp_w, &mg->resp_v,
-                      &mg->rgrad_w, &mg->rgrad_v};
+  cudaStreamSynchronize(mg->st2);
+  for (int b = 0; b < 2; ++b) {
+    XfDevBuf* pb[] = {&mg->d_set[b], &mg->d_keys[b], &mg->d_w[b], &mg->d_v[b], &mg->d_gw[b], &mg->d_gv[b],
+                      &mg->grad_w[b], &mg->grad_v[b], &mg->bucket_cnt[b]};
+    for (XfDevBuf* x : pb) x->release();
+    if (mg->ev_free[b]) cudaEventDestroy(mg->ev_free[b]);
+  }
+  XfDevBuf* bufs[] = {&mg->all_counts, &mg->recv_keys, &mg->recv_slots, &mg->resp_w, &mg->resp_v, &mg->rgrad_w, &mg->rgrad_v};
   for (XfDevBuf* b : bufs) b->release();
+  if (mg->st2) cudaStreamDestroy(mg->st2);
   if (mg->h_counts) cudaFreeHost(mg->h_counts);
   for (auto& e : mg->tev) cudaEventDestroy(e);
   delete mg;
@@ -366,23 +389,36 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
   cudaStream_t st = t->stream;
   const int S = mg->S;
   const size_t K = (size_t)t->view.K;
-  const XfWorkSet& ws = mg->ws;
+  const int cur = (int)(mg->step_no++ & 1);
+  const XfWorkSet& ws = mg->ws2[cur];
+  // With a second communicator the dedup of this batch and its bucket-size allgather run on their own
+  // stream, concurrently with whatever the previous step still has queued on the table stream
+  // (gradient exchange, owner updates).  Without it everything stays on the table stream.
+  const bool overlap = c->nccl2 != nullptr;
+  cudaStream_t sd = overlap ? mg->st2 : st;
+  ncclComm_t cd = overlap ? c->nccl2 : c->nccl;
 
   // ---- worker: clear the set (one streaming memset), dedup + number + bucket by owner
-  XF_MG_MARK(0);
-  XF_CUDA_TRY(cudaMemsetAsync(mg->d_set.p, 0xFF, mg->set_bytes, st));
-  XF_CUDA_TRY(cudaMemsetAsync(mg->bucket_cnt.p, 0, (size_t)S * 4, st));
+  if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) cudaEventRecord(mg->tev[mg->tsteps * 11 + 0], sd);
+  if (overlap) {
+    XF_CUDA_TRY(cudaStreamWaitEvent(sd, mg->ev_free[cur], 0));
+    // the batch itself may still be on its way (host path: H2D on the trainer's copy stream)
+    if (tr->input_ready) XF_CUDA_TRY(cudaStreamWaitEvent(sd, tr->input_ready, 0));
+  }
+  tr->input_ready = nullptr;
+  XF_CUDA_TRY(cudaMemsetAsync(mg->d_set[cur].p, 0xFF, mg->set_bytes, sd));
+  XF_CUDA_TRY(cudaMemsetAsync(mg->bucket_cnt[cur].p, 0, (size_t)S * 4, sd));
   if (nnz) {
     const uint32_t per_block = XF_WS_BLOCK * XF_WS_TOK;
-    xf_k_ws_dedup<<<(nnz + per_block - 1) / per_block, XF_WS_BLOCK, 0, st>>>(ws, d_keys, nnz, mg->width, S,
-                                                                              mg->bucket_cnt.as<uint32_t>());
+    xf_k_ws_dedup<<<(nnz + per_block - 1) / per_block, XF_WS_BLOCK, 0, sd>>>(ws, d_keys, nnz, mg->width, S,
+                                                                              mg->bucket_cnt[cur].as<uint32_t>());
     ++tr->launches;
   }
   // ---- bucket sizes of every rank (the only host sync of the step)
-  XF_MG_MARK(1);
-  XF_NCCL_TRY(g_nccl.AllGather(mg->bucket_cnt.p, mg->all_counts.p, (size_t)S, ncclUint32, c->nccl, st));
-  XF_CUDA_TRY(cudaMemcpyAsync(mg->h_counts, mg->all_counts.p, (size_t)S * S * 4, cudaMemcpyDeviceToHost, st));
-  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) cudaEventRecord(mg->tev[mg->tsteps * 11 + 1], sd);
+  XF_NCCL_TRY(g_nccl.AllGather(mg->bucket_cnt[cur].p, mg->all_counts.p, (size_t)S, ncclUint32, cd, sd));
+  XF_CUDA_TRY(cudaMemcpyAsync(mg->h_counts, mg->all_counts.p, (size_t)S * S * 4, cudaMemcpyDeviceToHost, sd));
+  XF_CUDA_TRY(cudaStreamSynchronize(sd));
   uint64_t n_send = 0, n_recv = 0;
   XfBucketCounts bc;
   memset(&bc, 0, sizeof(bc));
@@ -438,21 +474,23 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
   ++tr->launches;
   XF_MG_MARK(7);
   if (mode != 0) {
+    XF_CUDA_TRY(cudaEventRecord(mg->ev_free[cur], st));
     XF_CUDA_TRY(cudaGetLastError());
     return XF_OK;  // forward only: nothing was accumulated
   }
   if (n_send) {
     dim3 grid((unsigned)xf_grid_for((uint64_t)max_bucket * (K + 1), 256, 4), (unsigned)S);
-    xf_k_ws_grads<<<grid, 256, 0, st>>>(ws, bc, (double)rows, 1, mg->grad_w.as<float>(),
-                                        K ? mg->grad_v.as<float>() : nullptr);
+    xf_k_ws_grads<<<grid, 256, 0, st>>>(ws, bc, (double)rows, 1, mg->grad_w[cur].as<float>(),
+                                        K ? mg->grad_v[cur].as<float>() : nullptr);
     ++tr->launches;
   }
 
   // ---- all-to-all #3: gradients to the owners (the Push, kv_app.h:110-118)
   XF_MG_MARK(8);
-  XF_TRY(xf_all_to_all(c, mg->grad_w.p, mg->send_off, mg->send_cnt, mg->rgrad_w.p, mg->recv_off, mg->recv_cnt, 4, 1, st));
+  XF_TRY(xf_all_to_all(c, mg->grad_w[cur].p, mg->send_off, mg->send_cnt, mg->rgrad_w.p, mg->recv_off, mg->recv_cnt, 4, 1, st));
   if (K)
-    XF_TRY(xf_all_to_all(c, mg->grad_v.p, mg->send_off, mg->send_cnt, mg->rgrad_v.p, mg->recv_off, mg->recv_cnt, 4, K, st));
+    XF_TRY(xf_all_to_all(c, mg->grad_v[cur].p, mg->send_off, mg->send_cnt, mg->rgrad_v.p, mg->recv_off, mg->recv_cnt, 4, K, st));
+  XF_CUDA_TRY(cudaEventRecord(mg->ev_free[cur], st));  // work set `cur` and its gradient buffers are free again
   // ---- owner: Push handler, one optimizer step per (source, key), sources in rank order
   XF_MG_MARK(9);
   if (pm) XF_CUDA_TRY(cudaEventRecord(pm[2], st));

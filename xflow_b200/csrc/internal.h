@@ -95,6 +95,7 @@ struct xf_trainer {
   uint32_t last_rows = 0;
   uint64_t launches = 0;
   void* mg = nullptr;                   // multi-GPU exchange state (comm.cu)
+  cudaEvent_t input_ready = nullptr;    // set by the host-batch paths: H2D of the batch about to be stepped
   // optional per-kernel timing (xf_trainer_set_profile): events around the kernels of each step
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;  // 4 marks per step: step kernel [0,1], optimizer kernel(s) [2,3]
