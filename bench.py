@@ -122,7 +122,7 @@ def make_ring(wl, rank, n_batches):
     for i in range(n_batches):
         rp, ids, lab = datagen.make_ids(seed=1 + 1000 * rank + i, rows=wl["batch"], nnz_per_row=wl["nnz"],
                                         id_space=wl["id_space"], dist=wl["dist"], zipf_s=1.05)
-        ring.append((rp, api.hash_decimal_ids(ids), lab))
+        ring.append((rp, api.hash_decimal_ids(ids), lab, ids.astype(np.uint32)))
     return ring
 
 
@@ -245,12 +245,13 @@ def main():
     ring = make_ring(wl, rank, RING)
     # device-resident copies (raw bytes; torch is only the allocator here)
     dev = []
-    for rp, keys, lab in ring:
+    for rp, keys, lab, ids in ring:
         dev.append(tuple(torch.from_numpy(a.view(np.uint8)).cuda() for a in (rp, keys, lab)))
-    # page-locked host copies for the end-to-end leg
+    # page-locked host copies for the end-to-end legs: CSR of u32 feature ids (hashed to keys on the
+    # device, the loader's hashing moved to the GPU) and, for comparison, CSR of ready-made u64 keys
     pin = []
-    for rp, keys, lab in ring:
-        pin.append(tuple(torch.from_numpy(a.view(np.uint8)).pin_memory() for a in (rp, keys, lab)))
+    for rp, keys, lab, ids in ring:
+        pin.append(tuple(torch.from_numpy(a.view(np.uint8)).pin_memory() for a in (rp, keys, lab, ids)))
     results = torch.zeros(max(args.steps, 1), dtype=torch.float32).pin_memory()
 
     def barrier():
@@ -289,30 +290,36 @@ def main():
         tr.set_profile(False)
         st1 = tr.stats()
         launches = tr.launches() - l0
-        # ---------------- end-to-end timed region (host batches, H2D + result D2H every step)
-        for i in range(args.warmup):
-            p = pin[i % RING]
-            tr.step_host_async(p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), B, nnz, results.data_ptr())
-        tr.sync()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for i in range(args.steps):
-            p = pin[i % RING]
-            tr.step_host_async(p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), B, nnz,
-                               results.data_ptr() + 4 * i)
-        f1.record(stream)
-        tr.sync()
-        barrier()
-        ms_e2e = f0.elapsed_time(f1)
+        # ---------------- end-to-end timed regions (host batches, H2D + result D2H every step)
+        def e2e_leg(use_ids):
+            def one(i, out):
+                p = pin[i % RING]
+                if use_ids:
+                    tr.step_host_ids_async(p[0].data_ptr(), p[3].data_ptr(), p[2].data_ptr(), B, nnz, out)
+                else:
+                    tr.step_host_async(p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), B, nnz, out)
+            for i in range(args.warmup):
+                one(i, results.data_ptr())
+            tr.sync()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for i in range(args.steps):
+                one(i, results.data_ptr() + 4 * i)
+            f1.record(stream)
+            tr.sync()
+            barrier()
+            return f0.elapsed_time(f1)
+        ms_e2e_keys = e2e_leg(False)
+        ms_e2e = e2e_leg(True)
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_e2e_keys], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_e2e_keys = float(t[0]), float(t[1]), float(t[2])
     assert np.isfinite(results[: args.steps].numpy()).all()
 
     if rank == 0:
@@ -324,18 +331,21 @@ def main():
         b_step, b_update = algorithmic_bytes(wl, B, nnz, U)
         t_step = prof["step_ms"] / max(prof["steps"], 1) * 1e-3
         t_upd = prof["update_ms"] / max(prof["steps"], 1) * 1e-3
-        if t_upd > 0:
+        if t_upd > 0.05 * t_step:
             kern = [("xf_k_step (fused pull+forward+gradient)", b_step, t_step),
                     ("xf_k_update (FTRL over touched rows)", b_update, t_upd)]
         else:
             # LR tables fold the optimizer step into the next touch of a row: one kernel does all of it
             kern = [("xf_k_step_lr_lazy (pull+forward+gradient+optimizer in one kernel)", b_step + b_update, t_step)]
         dom = max(kern, key=lambda k: k[2])
-        traffic = None
+        traffic = sectors = ceiling = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(args.workload, {}).get(dom[0].split(" ")[0])
+                tj = json.load(open(tpath))
+                traffic = tj.get(args.workload, {}).get(dom[0].split(" ")[0])
+                sectors = tj.get(args.workload, {}).get(dom[0].split(" ")[0] + "_dram_sectors")
+                ceiling = tj.get("random_sector_ceiling_gsectors_per_s")
             except Exception:
                 traffic = None
         roofline = {
@@ -347,6 +357,12 @@ def main():
             "step_algorithmic_bytes": b_step + b_update, "step_gbs": (b_step + b_update) / (ms * 1e-3 / steps) / 1e9,
             "step_frac": (b_step + b_update) / (ms * 1e-3 / steps) / 1e9 / peak,
             "unique_keys_per_batch": U,
+            # the access pattern is one random 32-byte sector per table row: the practical ceiling is the
+            # measured random-sector request rate (tools/randsector.cu, profiles/r01_randsector.md), not
+            # the streaming-copy bandwidth `peak` above
+            "random_sector_ceiling_gsectors_per_s": ceiling,
+            "dram_sector_requests_per_launch": sectors,
+            "frac_of_random_sector_ceiling": (sectors / dom[2] / 1e9 / ceiling) if (sectors and ceiling) else None,
         }
         line = {
             "metric": "training examples/sec", "value": value, "unit": "examples/s", "n_gpus": world,
@@ -361,8 +377,12 @@ def main():
                        "parallelism": "dp%d, table range-sharded over %d GPU(s)" % (world, world)},
             "clocks": sampler.summary(t_w0, t_w1),
             "e2e": {"value": e2e_value, "unit": "examples/s", "ms_per_step": ms_e2e / steps,
-                    "h2d_bytes_per_step": (B + 1) * 4 + nnz * 8 + B, "d2h_bytes_per_step": 4,
-                    "api": "xf_trainer_step_host_async (C ABI), page-locked host CSR batches"},
+                    "h2d_bytes_per_step": (B + 1) * 4 + nnz * 4 + B, "d2h_bytes_per_step": 4,
+                    "api": "xf_trainer_step_host_ids_async (C ABI): page-locked host CSR of u32 feature ids, "
+                           "hashed to keys on the device",
+                    "with_prehashed_u64_keys": {"value": world * B * steps / (ms_e2e_keys * 1e-3),
+                                                "h2d_bytes_per_step": (B + 1) * 4 + nnz * 8 + B,
+                                                "api": "xf_trainer_step_host_async"}},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }

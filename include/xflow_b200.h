@@ -174,6 +174,15 @@ XF_DLL int xf_trainer_wait_uploads(xf_trainer* tr);
 XF_DLL int xf_trainer_step_host_async(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys,
                                       const uint8_t* labels, uint32_t rows, uint32_t nnz,
                                       float* pinned_abs_loss_sum);
+/* Same as xf_trainer_step_host_async for callers that hold integer feature ids instead of hashed keys:
+ * ids[nnz] are u32 ids whose DECIMAL STRING is what the reference's loader would hash
+ * (load_data_from_disk.cc:151); the device computes keys = std::hash(decimal string) itself (ingest.cu),
+ * so only 4 bytes per token cross PCIe.  Buffers must be page-locked. */
+XF_DLL int xf_trainer_step_host_ids_async(xf_trainer* tr, const uint32_t* row_ptr, const uint32_t* ids,
+                                          const uint8_t* labels, uint32_t rows, uint32_t nnz,
+                                          float* pinned_abs_loss_sum);
+/* keys[i] = std::hash<std::string>(decimal string of ids[i]) on DEVICE arrays (stream: cudaStream_t or NULL) */
+XF_DLL int xf_hash_decimal_ids_device(const uint32_t* d_ids, uint64_t n, uint64_t* d_keys, void* cuda_stream);
 /* Per-kernel device timing for roofline reporting.  on != 0: record CUDA events around the kernels
  * of every following step (on the table's stream).  xf_trainer_profile syncs and returns, summed
  * over the profiled steps since the last call: ms[0] = fused step kernel, ms[1] = optimizer kernel

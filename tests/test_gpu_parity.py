@@ -269,3 +269,34 @@ def test_full_size_batch_properties():
     # a second, identical batch: every key already present -> size unchanged, unique count doubles
     tr.step_host(rp, keys, lab)
     assert gt.size() == uk.size and tr.stats()["unique_keys"] == 2 * uk.size
+
+
+def test_device_id_hashing_is_bit_exact_and_ids_path_trains_identically():
+    """ingest.cu: keys made on the device from u32 ids == std::hash of the decimal strings; the ids entry
+    point leaves the same table as the keys entry point."""
+    import torch
+    rng = np.random.default_rng(7)
+    ids = rng.integers(0, 2 ** 32, 200000, dtype=np.uint64).astype(np.uint32)
+    ids[:6] = [0, 9, 10, 99, 100, 4294967295]
+    d_ids = torch.from_numpy(ids.view(np.int32)).cuda()
+    d_keys = torch.empty(ids.size, dtype=torch.int64, device="cuda")
+    assert api.lib().xf_hash_decimal_ids_device(d_ids.data_ptr(), ids.size, d_keys.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    got = d_keys.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, O.hash_decimal_ids(ids.astype(np.uint64)))
+    assert int(got[5]) == O.std_hash(b"4294967295")
+
+    B, d = 4096, 32
+    rp, idv, lab = datagen.make_ids(3, B, d, 50000)
+    keys = api.hash_decimal_ids(idv)
+    ta, tb = api.Table(), api.Table()
+    tra, trb = api.Trainer(ta, max_rows=B, max_nnz=B * d), api.Trainer(tb, max_rows=B, max_nnz=B * d)
+    pin = [torch.from_numpy(a.view(np.uint8)).pin_memory() for a in (rp, idv.astype(np.uint32), lab)]
+    for _ in range(3):
+        tra.step_host(rp, keys, lab)
+        trb.step_host_ids_async(pin[0].data_ptr(), pin[1].data_ptr(), pin[2].data_ptr(), B, B * d)
+    trb.sync()
+    uk = np.unique(keys)
+    a, b = ta.export(uk), tb.export(uk)
+    for k in ("w", "nw", "zw", "present"):
+        assert np.array_equal(a[k], b[k]), k

@@ -71,6 +71,8 @@ SIGNATURES = {
     "xf_trainer_sync": (_i, [_vp]),
     "xf_trainer_wait_uploads": (_i, [_vp]),
     "xf_trainer_step_host_async": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "xf_trainer_step_host_ids_async": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "xf_hash_decimal_ids_device": (_i, [_vp, _u64, _vp, _vp]),
     "xf_trainer_set_profile": (_i, [_vp, _i]),
     "xf_trainer_profile": (_i, [_vp, _vp, _vp]),
     "xf_host_alloc": (_i, [_vp, _u64]),
@@ -335,6 +337,11 @@ class Trainer:
         """Pipelined step on page-locked buffers given by address; never blocks on the device."""
         _check(lib().xf_trainer_step_host_async(self.h, _p(row_ptr_addr), _p(keys_addr), _p(labels_addr), rows, nnz,
                                                 _p(out_addr) if out_addr else None))
+
+    def step_host_ids_async(self, row_ptr_addr, ids_addr, labels_addr, rows, nnz, out_addr=None):
+        """Like step_host_async but with u32 feature ids (hashed to keys on the device)."""
+        _check(lib().xf_trainer_step_host_ids_async(self.h, _p(row_ptr_addr), _p(ids_addr), _p(labels_addr), rows,
+                                                    nnz, _p(out_addr) if out_addr else None))
 
     def wait_uploads(self):
         _check(lib().xf_trainer_wait_uploads(self.h))

@@ -156,12 +156,37 @@ int xf_table::next_seq() {
 
 int xf_table::ensure_room(uint64_t incoming) {
   const uint64_t cap = view.mask + 1;
+  // --- fast path: bound from the asynchronous read-backs, no host sync
+  cum_incoming += incoming;
+  if (h_size_ring) {
+    for (int i = 0; i < 4; ++i)
+      if (size_inflight[i] && cudaEventQuery(size_ev[i]) == cudaSuccess) {
+        size_inflight[i] = false;
+        if (size_issued_at[i] >= known_at) { known_at = size_issued_at[i]; known_size = h_size_ring[i]; }
+      }
+    cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
+    const uint64_t bound = known_size + (cum_incoming - known_at);
+    const int slot = size_next;
+    if (!size_inflight[slot]) {
+      // reflects every kernel enqueued so far, i.e. everything but this step's own `incoming`
+      if (cudaMemcpyAsync(h_size_ring + slot, d_size, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream) ==
+              cudaSuccess && cudaEventRecord(size_ev[slot], stream) == cudaSuccess) {
+        size_inflight[slot] = true;
+        size_issued_at[slot] = cum_incoming - incoming;
+        size_next = (slot + 1) & 3;
+      }
+    }
+    if (bound * 4 <= cap * 3) { size_bound = bound; return XF_OK; }  // load stays <= 0.75 even in the worst case
+  }
+  // --- slow path: read the exact size, grow to load <= 0.5 if needed
   size_bound += incoming;
-  if (size_bound * 2 <= cap) return XF_OK;
+  if (!h_size_ring && size_bound * 2 <= cap) return XF_OK;
   unsigned long long actual = 0;
   XF_CUDA_TRY(cudaMemcpyAsync(&actual, d_size, sizeof(actual), cudaMemcpyDeviceToHost, stream));
   XF_CUDA_TRY(cudaStreamSynchronize(stream));
   size_bound = actual + incoming;
+  known_size = actual;
+  known_at = cum_incoming - incoming;
   uint64_t want = cap;
   while (size_bound * 2 > want) want <<= 1;
   if (want != cap) XF_TRY(grow(want));
@@ -200,6 +225,8 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
   else v.v_init = (v.opt == XF_OPT_FTRL) ? XF_INIT_COUNTER : XF_INIT_DEFAULT;
   v.size = t->d_size;
   v.error = t->d_error;
+  XF_CUDA_TRY(cudaHostAlloc(&t->h_size_ring, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+  for (int i = 0; i < 4; ++i) XF_CUDA_TRY(cudaEventCreateWithFlags(&t->size_ev[i], cudaEventDisableTiming));
   // K == 0 (LR) tables fold the optimizer step into the next touch of a row (step.cu); K > 0 tables
   // keep the separate optimizer kernel.  XFLOW_EAGER=1 forces the two-kernel path (A/B measurements).
   const char* eager = getenv("XFLOW_EAGER");
@@ -227,6 +254,8 @@ XF_DLL int xf_table_destroy(xf_table* t) {
   cudaFree(t->d_size);
   cudaFree(t->d_error);
   if (t->d_rows_by_seq) cudaFree(t->d_rows_by_seq);
+  if (t->h_size_ring) cudaFreeHost(t->h_size_ring);
+  for (int i = 0; i < 4; ++i) if (t->size_ev[i]) cudaEventDestroy(t->size_ev[i]);
   t->s_keys.release(); t->s_slots.release(); t->s_w.release(); t->s_v.release();
   t->s_nw.release(); t->s_zw.release(); t->s_nv.release(); t->s_zv.release(); t->s_present.release();
   if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
@@ -549,7 +578,7 @@ XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
   if (tr->mg) xf_mg_destroy(tr);
   for (int i = 0; i < 2; ++i) {
     XfBatchBuf& b = tr->buf[i];
-    b.row_ptr.release(); b.keys.release(); b.labels.release();
+    b.row_ptr.release(); b.keys.release(); b.labels.release(); b.ids.release();
     b.h_row_ptr.release(); b.h_keys.release(); b.h_labels.release();
     cudaEventDestroy(b.copied); cudaEventDestroy(b.consumed); cudaEventDestroy(b.staged);
   }
@@ -799,6 +828,49 @@ XF_DLL int xf_trainer_step_host_async(xf_trainer* tr, const uint32_t* row_ptr, c
   ++tr->step_index;
   XF_TRY(xf_upload_batch(tr, b, row_ptr, keys, labels, rows, nnz));
   cudaStream_t st = tr->table->stream;
+  XF_CUDA_TRY(cudaMemsetAsync(tr->d_abs_loss + slot, 0, sizeof(float), st));
+  XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows,
+                             nnz, 0, tr->d_abs_loss + slot));
+  XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
+  if (pinned_abs_loss_sum)
+    XF_CUDA_TRY(cudaMemcpyAsync(pinned_abs_loss_sum, tr->d_abs_loss + slot, sizeof(float), cudaMemcpyDeviceToHost, st));
+  ++tr->n_steps;
+  tr->n_rows += rows;
+  tr->n_nnz += nnz;
+  tr->last_rows = rows;
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_step_host_ids_async(xf_trainer* tr, const uint32_t* row_ptr, const uint32_t* ids,
+                                          const uint8_t* labels, uint32_t rows, uint32_t nnz,
+                                          float* pinned_abs_loss_sum) {
+  if (!tr || !row_ptr || (!ids && nnz) || !labels) return XF_ERR_ARG;
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  if (rows == 0) return XF_OK;
+  if (!xf_is_pinned(row_ptr) || !xf_is_pinned(ids) || !xf_is_pinned(labels) ||
+      (pinned_abs_loss_sum && !xf_is_pinned(pinned_abs_loss_sum))) {
+    xf_set_error("xf_trainer_step_host_ids_async needs page-locked host buffers");
+    return XF_ERR_ARG;
+  }
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const int slot = (int)(tr->step_index & 1);
+  XfBatchBuf& b = tr->buf[slot];
+  ++tr->step_index;
+  // upload row_ptr, ids (4 B/token instead of 8 B keys) and labels; hash on the device
+  XF_CUDA_TRY(cudaStreamWaitEvent(tr->copy_stream, b.consumed, 0));
+  XF_TRY(b.row_ptr.ensure(((size_t)rows + 1) * 4));
+  XF_TRY(b.ids.ensure((size_t)nnz * 4));
+  XF_TRY(b.keys.ensure((size_t)nnz * 8));
+  XF_TRY(b.labels.ensure(rows));
+  XF_CUDA_TRY(cudaMemcpyAsync(b.row_ptr.p, row_ptr, ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, tr->copy_stream));
+  XF_CUDA_TRY(cudaMemcpyAsync(b.ids.p, ids, (size_t)nnz * 4, cudaMemcpyHostToDevice, tr->copy_stream));
+  XF_CUDA_TRY(cudaMemcpyAsync(b.labels.p, labels, rows, cudaMemcpyHostToDevice, tr->copy_stream));
+  XF_TRY(xf_launch_hash_ids(b.ids.as<uint32_t>(), nnz, b.keys.as<uint64_t>(), tr->copy_stream));
+  ++tr->launches;
+  XF_CUDA_TRY(cudaEventRecord(b.copied, tr->copy_stream));
+  cudaStream_t st = tr->table->stream;
+  XF_CUDA_TRY(cudaStreamWaitEvent(st, b.copied, 0));
+  tr->input_ready = b.copied;
   XF_CUDA_TRY(cudaMemsetAsync(tr->d_abs_loss + slot, 0, sizeof(float), st));
   XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows,
                              nnz, 0, tr->d_abs_loss + slot));

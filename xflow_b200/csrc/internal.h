@@ -53,7 +53,15 @@ struct xf_table {
   bool own_stream = true;
   unsigned long long* d_size = nullptr;
   int* d_error = nullptr;
-  uint64_t size_bound = 0;   // host-side upper bound on the number of live keys
+  uint64_t size_bound = 0;   // host-side upper bound on the number of live keys (sync path)
+  // asynchronous size read-back (no host sync in steady state): the device counter is copied to a
+  // pinned ring after every step; bound = last completed reading + keys submitted since it was issued
+  unsigned long long* h_size_ring = nullptr;
+  cudaEvent_t size_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint64_t size_issued_at[4] = {0, 0, 0, 0};
+  bool size_inflight[4] = {false, false, false, false};
+  int size_next = 0;
+  uint64_t cum_incoming = 0, known_size = 0, known_at = 0;
   uint64_t launches = 0;
   int refs = 1;              // the creator + every trainer bound to the table (destroy order is free)
   // lazy ("update on next touch") tables: batch sequence number and the per-batch row counts
@@ -71,7 +79,7 @@ struct xf_table {
 };
 
 struct XfBatchBuf {
-  XfDevBuf row_ptr, keys, labels;
+  XfDevBuf row_ptr, keys, labels, ids;
   XfPinBuf h_row_ptr, h_keys, h_labels;
   cudaEvent_t copied = nullptr;   // H2D of this buffer finished (copy stream)
   cudaEvent_t consumed = nullptr; // kernels reading this buffer finished (compute stream)
@@ -101,6 +109,9 @@ struct xf_trainer {
   std::vector<cudaEvent_t> prof_events;  // 4 marks per step: step kernel [0,1], optimizer kernel(s) [2,3]
   size_t prof_used = 0;
 };
+
+// ingest.cu
+int xf_launch_hash_ids(const uint32_t* d_ids, uint32_t n, uint64_t* d_keys, cudaStream_t st);
 
 // multi-GPU pieces implemented in comm.cu
 int xf_mg_create(xf_trainer* tr);
