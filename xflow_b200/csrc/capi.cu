@@ -637,7 +637,9 @@ static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const 
     XF_CUDA_TRY(cudaGetLastError());
     return XF_OK;
   }
-  xf_launch_step(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
+  const uint32_t extra = xf_step_touched_extra(t->view.K, (int)rows);
+  XF_TRY(tr->touched.ensure(((size_t)nnz + extra) * 4));
+  xf_launch_step(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(), nnz,
                  (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
                  mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
   ++tr->launches;
@@ -647,7 +649,8 @@ static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const 
   }
   if (mode == 0) {
     // Push + server-side optimizer: one FTRL/SGD step per touched key with g / rows
-    xf_launch_update_touched(t->view, tr->touched.as<uint32_t>(), nnz, (double)rows, tr->d_unique_total, st);
+    xf_launch_update_touched(t->view, tr->touched.as<uint32_t>(), (uint64_t)nnz + extra, (double)rows,
+                             tr->d_unique_total, st);
     ++tr->launches;
   }
   if (prof) XF_CUDA_TRY(cudaEventRecord(pe[3], st));

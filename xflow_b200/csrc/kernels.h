@@ -11,8 +11,10 @@ int xf_tps_for(int K);
 
 void xf_launch_fill(const XfTableView& t, cudaStream_t st);
 void xf_launch_step(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* labels,
-                    int B, int mode, uint32_t* touched, float* loss_out, float* pctr_out, float* abs_loss_sum,
-                    cudaStream_t st);
+                    int B, int mode, uint32_t* touched, uint32_t nnz, float* loss_out, float* pctr_out,
+                    float* abs_loss_sum, cudaStream_t st);
+// FM step: shared-memory hot-key cache; its flush uses touched[nnz .. nnz + xf_step_touched_extra)
+uint32_t xf_step_touched_extra(int K, int B);
 // touched[j] (one entry per token position) = slot of the key first touched by token j, else 0xFFFFFFFF
 void xf_launch_update_touched(const XfTableView& t, const uint32_t* touched, uint64_t nnz, double rows,
                               unsigned long long* unique_total, cudaStream_t st);
