@@ -339,6 +339,7 @@ XF_DLL int xf_table_push_device(xf_table* t, const uint64_t* d_keys, uint64_t n,
 
 XF_DLL int xf_table_pull(xf_table* t, const uint64_t* keys, uint64_t n, float* w_out, float* v_out) {
   if (!t || (!keys && n)) return XF_ERR_ARG;
+  std::lock_guard<std::mutex> host_lock(t->host_mu);
   if (n == 0) return XF_OK;
   XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
   const int K = t->view.K;
@@ -354,6 +355,7 @@ XF_DLL int xf_table_pull(xf_table* t, const uint64_t* keys, uint64_t n, float* w
 
 XF_DLL int xf_table_push(xf_table* t, const uint64_t* keys, uint64_t n, const float* gw, const float* gv) {
   if (!t || (!keys && n)) return XF_ERR_ARG;
+  std::lock_guard<std::mutex> host_lock(t->host_mu);
   if (n == 0) return XF_OK;
   XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
   const int K = t->view.K;
@@ -384,6 +386,7 @@ static int xf_h2d_opt(XfDevBuf& b, const float* src, size_t count, cudaStream_t 
 XF_DLL int xf_table_import(xf_table* t, const uint64_t* keys, uint64_t n, const float* w, const float* nw,
                            const float* zw, const float* v, const float* nv, const float* zv) {
   if (!t || (!keys && n)) return XF_ERR_ARG;
+  std::lock_guard<std::mutex> host_lock(t->host_mu);
   if (n == 0) return XF_OK;
   XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
   const size_t K = (size_t)t->view.K;
@@ -408,6 +411,7 @@ XF_DLL int xf_table_import(xf_table* t, const uint64_t* keys, uint64_t n, const 
 XF_DLL int xf_table_export(xf_table* t, const uint64_t* keys, uint64_t n, float* w, float* nw, float* zw,
                            float* v, float* nv, float* zv, uint8_t* present) {
   if (!t || (!keys && n)) return XF_ERR_ARG;
+  std::lock_guard<std::mutex> host_lock(t->host_mu);
   if (n == 0) return XF_OK;
   XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
   const size_t K = (size_t)t->view.K;
@@ -442,6 +446,7 @@ XF_DLL int xf_table_export(xf_table* t, const uint64_t* keys, uint64_t n, float*
 
 XF_DLL int xf_table_list_keys(xf_table* t, uint64_t* keys_out, uint64_t max_keys, uint64_t* n_out) {
   if (!t || !n_out) return XF_ERR_ARG;
+  std::lock_guard<std::mutex> host_lock(t->host_mu);
   XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
   XF_TRY(t->s_keys.ensure(std::max<uint64_t>(max_keys, 1) * 8));
   unsigned long long* d_count = nullptr;
@@ -544,14 +549,13 @@ XF_DLL int xf_trainer_create(xf_trainer** out, xf_table* table, xf_comm* comm, c
     XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->buf[i].consumed, cudaEventDisableTiming));
     XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->buf[i].staged, cudaEventDisableTiming));
   }
-  XF_TRY(tr->touched.ensure((size_t)cfg->max_nnz * 4));
+  // one slot per token position + the FM hot-key cache's flush positions (grid x NC, see step.cu)
+  XF_TRY(tr->touched.ensure(((size_t)cfg->max_nnz + xf_step_touched_extra(table->view.K, (int)cfg->max_rows)) * 4));
   XF_TRY(tr->loss.ensure((size_t)cfg->max_rows * 4));
   XF_TRY(tr->pctr.ensure((size_t)cfg->max_rows * 4));
-  XF_CUDA_TRY(cudaMalloc(&tr->d_touched_cnt, sizeof(unsigned int)));
   XF_CUDA_TRY(cudaMalloc(&tr->d_unique_total, sizeof(unsigned long long)));
   XF_CUDA_TRY(cudaMalloc(&tr->d_abs_loss, 2 * sizeof(float)));
   XF_CUDA_TRY(cudaHostAlloc(&tr->h_abs_loss, 2 * sizeof(float), cudaHostAllocDefault));
-  XF_CUDA_TRY(cudaMemsetAsync(tr->d_touched_cnt, 0, sizeof(unsigned int), table->stream));
   XF_CUDA_TRY(cudaMemsetAsync(tr->d_unique_total, 0, sizeof(unsigned long long), table->stream));
   XF_CUDA_TRY(cudaMemsetAsync(tr->d_abs_loss, 0, 2 * sizeof(float), table->stream));
   XF_CUDA_TRY(cudaStreamSynchronize(table->stream));
@@ -583,7 +587,7 @@ XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
     cudaEventDestroy(b.copied); cudaEventDestroy(b.consumed); cudaEventDestroy(b.staged);
   }
   tr->touched.release(); tr->loss.release(); tr->pctr.release();
-  cudaFree(tr->d_touched_cnt); cudaFree(tr->d_unique_total); cudaFree(tr->d_abs_loss);
+  cudaFree(tr->d_unique_total); cudaFree(tr->d_abs_loss);
   cudaFreeHost(tr->h_abs_loss);
   cudaStreamDestroy(tr->copy_stream);
   for (cudaEvent_t e : tr->prof_events) cudaEventDestroy(e);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -69,7 +70,9 @@ struct xf_table {
   uint32_t* d_rows_by_seq = nullptr;
   size_t rows_cap = 0;
   int next_seq();            // advances seq, growing rows_by_seq when needed
-  // scratch for the host-pointer API
+  // scratch for the host-pointer API (pull/push/import/export on host arrays); like KVWorker::Push/Pull
+  // (kv_app.h:110-165) those entry points may be called from several threads: serialised by this mutex
+  std::mutex host_mu;
   XfDevBuf s_keys, s_slots, s_w, s_v, s_nw, s_zw, s_nv, s_zv, s_present;
 
   int alloc_table(uint64_t capacity);
@@ -94,7 +97,6 @@ struct xf_trainer {
   XfBatchBuf buf[2];
   uint64_t step_index = 0;
   XfDevBuf touched, loss, pctr;
-  unsigned int* d_touched_cnt = nullptr;
   unsigned long long* d_unique_total = nullptr;
   float* d_abs_loss = nullptr;          // 2 slots
   float* h_abs_loss = nullptr;          // pinned, 2 slots

@@ -3,12 +3,7 @@
 // reference's FM term is a per-row scalar, fm_worker.cc:177-196), so no tensor-core code.
 //
 //   xf_k_fill               table initialisation (EMPTY keys, g = -0.0f)
-//   xf_k_step<FM,VEC>       FUSED worker step: CSR -> probe/insert -> gather w(,v) -> per-row
-//                           warp-segmented sums -> sigmoid -> residual -> per-key gradient accumulate
-//                           into the row (L2 atomics on the sector just loaded) -> "touched" list.
-//                           = LRWorker::update's pull + calculate_loss + calculate_gradient
-//                           (lr_worker.cc:121-177) / FMWorker's (fm_worker.cc:126-245) without the
-//                           sort/unique/merge-join: the table row itself is the per-key accumulator.
+//   (the fused worker step lives in step.cu / step_lazy.cu)
 //   xf_k_update<VEC,SLOTG>  optimizer step over a list of rows (FTRL ftrl.h:54-79,112-146 /
 //                           SGD sgd.h:46-59,90-103), gradient either from the row's accumulators
 //                           (fused step; divides by the slice row count) or from a pushed array.
@@ -16,14 +11,11 @@
 //   xf_k_gather             slot rows -> w / v arrays                 } import / export pieces
 //   xf_k_import / xf_k_export
 //   xf_k_rehash             growth
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "kernels.h"
 #include "table.cuh"
-
-namespace cg = cooperative_groups;
 
 // -------------------------------------------------------------------------------------------------
 // fill
@@ -46,11 +38,6 @@ __global__ void xf_k_fill(uint8_t* base, uint64_t cap, uint32_t stride) {
 // -------------------------------------------------------------------------------------------------
 // vector helpers for the latent blocks
 // -------------------------------------------------------------------------------------------------
-template <int VEC> struct XfVec;
-template <> struct XfVec<4> { typedef float4 T; };
-template <> struct XfVec<2> { typedef float2 T; };
-template <> struct XfVec<1> { typedef float T; };
-
 template <int VEC>
 __device__ __forceinline__ void xf_ldv(const float* p, float (&o)[VEC]) {
   if (VEC == 4) { float4 t = __ldcg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1 % VEC] = t.y; o[2 % VEC] = t.z; o[3 % VEC] = t.w; }
@@ -63,20 +50,6 @@ __device__ __forceinline__ void xf_stv(float* p, const float (&o)[VEC]) {
   else if (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1 % VEC]);
   else *p = o[0];
 }
-// vector reduction (no return) into global memory: one L2 atomic transaction per 8/16 bytes
-template <int VEC>
-__device__ __forceinline__ void xf_redv(float* p, const float (&o)[VEC]) {
-  if (VEC == 4) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(o[0]), "f"(o[1 % VEC]),
-                 "f"(o[2 % VEC]), "f"(o[3 % VEC])
-                 : "memory");
-  } else if (VEC == 2) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(o[0]), "f"(o[1 % VEC]) : "memory");
-  } else {
-    atomicAdd(p, o[0]);
-  }
-}
-
 // -------------------------------------------------------------------------------------------------
 // optimizer step over a list of rows
 // -------------------------------------------------------------------------------------------------

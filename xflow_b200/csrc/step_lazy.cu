@@ -41,6 +41,7 @@ __device__ __forceinline__ uint32_t xf_ld_tag(const uint8_t* rowp) {
 __device__ __forceinline__ float xf_reload_w(const uint8_t* rowp) {
   uint64_t q0, q1, q2, q3;
   asm volatile("ld.volatile.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(rowp));
+  (void)q0; (void)q2; (void)q3;
   return __uint_as_float((uint32_t)q1);
 }
 
