@@ -95,6 +95,7 @@ class XF_CXX_API WorkerBase {
   WorkerBase(const char* train_file, const char* test_file, int model);
   const char* model_name() const { return model_ == XF_MODEL_LR ? "LR" : "FM"; }
   void ensure_trainer(uint32_t rows, uint32_t nnz);
+  void ensure_trainer_for_block(uint64_t bytes);
 
   int model_;
   std::string train_file_path, test_file_path;

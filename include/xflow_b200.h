@@ -183,6 +183,16 @@ XF_DLL int xf_trainer_step_host_ids_async(xf_trainer* tr, const uint32_t* row_pt
                                           float* pinned_abs_loss_sum);
 /* keys[i] = std::hash<std::string>(decimal string of ids[i]) on DEVICE arrays (stream: cudaStream_t or NULL) */
 XF_DLL int xf_hash_decimal_ids_device(const uint32_t* d_ids, uint64_t n, uint64_t* d_keys, void* cuda_stream);
+/* Device-side ingest of one text block (load_data_from_disk.cc:126-209 on the GPU, ingest.cu): uploads
+ * `len` bytes of "<label>\t<fgid>:<fid>:<val> ...\n" rows, parses them into a CSR batch that stays on
+ * the device, and reports its size.  xf_trainer_step_ingested / _predict_ingested then run the step on a
+ * row range [row_start, row_end) of that block (the reference's per-thread slices, lr_worker.cc:190-196). */
+XF_DLL int xf_trainer_ingest_text(xf_trainer* tr, const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz);
+XF_DLL int xf_trainer_step_ingested(xf_trainer* tr, uint32_t row_start, uint32_t row_end);
+/* copy the ingested block's CSR back to host arrays of rows+1 / nnz / rows elements (any may be NULL) */
+XF_DLL int xf_trainer_ingested_export(xf_trainer* tr, uint32_t* row_ptr_out, uint64_t* keys_out, uint8_t* labels_out);
+XF_DLL int xf_trainer_predict_ingested(xf_trainer* tr, uint32_t row_start, uint32_t row_end, float* pctr_out,
+                                       uint8_t* labels_out);
 /* Per-kernel device timing for roofline reporting.  on != 0: record CUDA events around the kernels
  * of every following step (on the table's stream).  xf_trainer_profile syncs and returns, summed
  * over the profiled steps since the last call: ms[0] = fused step kernel, ms[1] = optimizer kernel
@@ -214,6 +224,9 @@ XF_DLL int xf_loader_close(xf_loader* l);
  * *rows = 0 at end of file.  The CSR arrays stay valid until the next call. */
 XF_DLL int xf_loader_next(xf_loader* l, uint32_t* rows, uint32_t* nnz);
 XF_DLL int xf_loader_batch(xf_loader* l, const uint32_t** row_ptr, const uint64_t** keys, const uint8_t** labels);
+/* block formation only (load_data_from_disk.cc:108-124): the next block's raw text, for the device parser
+ * (xf_trainer_ingest_text).  *len = 0 at end of file.  The text stays valid until the next call. */
+XF_DLL int xf_loader_next_raw(xf_loader* l, const char** text, uint64_t* len);
 
 /* ------------------------------------------------------------------------------------------------
  * 5. Multi-GPU exchange (one process per GPU; NCCL over NVLink)

@@ -73,6 +73,11 @@ SIGNATURES = {
     "xf_trainer_step_host_async": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "xf_trainer_step_host_ids_async": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "xf_hash_decimal_ids_device": (_i, [_vp, _u64, _vp, _vp]),
+    "xf_trainer_ingest_text": (_i, [_vp, _vp, _u64, _vp, _vp]),
+    "xf_trainer_step_ingested": (_i, [_vp, _u32, _u32]),
+    "xf_trainer_ingested_export": (_i, [_vp, _vp, _vp, _vp]),
+    "xf_trainer_predict_ingested": (_i, [_vp, _u32, _u32, _vp, _vp]),
+    "xf_loader_next_raw": (_i, [_vp, _vp, _vp]),
     "xf_trainer_set_profile": (_i, [_vp, _i]),
     "xf_trainer_profile": (_i, [_vp, _vp, _vp]),
     "xf_host_alloc": (_i, [_vp, _u64]),
@@ -181,6 +186,13 @@ class Loader:
         keys = np.ctypeslib.as_array(C.cast(kp, C.POINTER(C.c_uint64)), (max(n, 1),))[:n].copy()
         labels = np.ctypeslib.as_array(C.cast(lp, C.POINTER(C.c_uint8)), (B,)).copy()
         return row_ptr, keys, labels
+
+
+    def next_raw(self):
+        """Block formation only: the next block's raw text (b"" at end of file)."""
+        text, n = C.c_void_p(), C.c_uint64()
+        _check(lib().xf_loader_next_raw(self.h, C.byref(text), C.byref(n)))
+        return C.string_at(text, n.value) if n.value else b""
 
 
 class Table:
@@ -342,6 +354,30 @@ class Trainer:
         """Like step_host_async but with u32 feature ids (hashed to keys on the device)."""
         _check(lib().xf_trainer_step_host_ids_async(self.h, _p(row_ptr_addr), _p(ids_addr), _p(labels_addr), rows,
                                                     nnz, _p(out_addr) if out_addr else None))
+
+    def ingest_text(self, text: bytes):
+        """Parse one text block on the device; returns (rows, nnz) of the CSR now resident there."""
+        rows, nnz = C.c_uint32(), C.c_uint32()
+        buf = C.create_string_buffer(text, len(text))
+        _check(lib().xf_trainer_ingest_text(self.h, C.cast(buf, C.c_void_p), len(text), C.byref(rows), C.byref(nnz)))
+        return rows.value, nnz.value
+
+    def ingested_export(self, rows, nnz):
+        rp = np.empty(rows + 1, np.uint32)
+        keys = np.empty(nnz, np.uint64)
+        lab = np.empty(rows, np.uint8)
+        _check(lib().xf_trainer_ingested_export(self.h, _p(rp), _p(keys), _p(lab)))
+        return rp, keys, lab
+
+    def step_ingested(self, row_start, row_end):
+        _check(lib().xf_trainer_step_ingested(self.h, row_start, row_end))
+
+    def predict_ingested(self, row_start, row_end):
+        n = row_end - row_start
+        p = np.empty(n, np.float32)
+        lab = np.empty(n, np.uint8)
+        _check(lib().xf_trainer_predict_ingested(self.h, row_start, row_end, _p(p), _p(lab)))
+        return p, lab
 
     def wait_uploads(self):
         _check(lib().xf_trainer_wait_uploads(self.h))

@@ -587,6 +587,8 @@ XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
     cudaEventDestroy(b.copied); cudaEventDestroy(b.consumed); cudaEventDestroy(b.staged);
   }
   tr->touched.release(); tr->loss.release(); tr->pctr.release();
+  tr->ing_text.release(); tr->ing_scratch.release(); tr->ing_row_ptr.release(); tr->ing_keys.release();
+  tr->ing_labels.release(); tr->ing_totals.release(); tr->ing_stage.release();
   cudaFree(tr->d_unique_total); cudaFree(tr->d_abs_loss);
   cudaFreeHost(tr->h_abs_loss);
   cudaStreamDestroy(tr->copy_stream);
@@ -889,6 +891,106 @@ XF_DLL int xf_trainer_step_host_ids_async(xf_trainer* tr, const uint32_t* row_pt
   tr->n_nnz += nnz;
   tr->last_rows = rows;
   return XF_OK;
+}
+
+XF_DLL int xf_trainer_ingest_text(xf_trainer* tr, const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz) {
+  if (!tr || (!text && len) || !rows || !nnz) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  cudaStream_t st = tr->table->stream;
+  // upper bounds for a block of `len` bytes: shortest row "0\ta:b:c\n" = 8 bytes, shortest extra token 6 bytes
+  const uint32_t max_rows = (uint32_t)std::min<uint64_t>(len / 2 + 2, tr->cfg.max_rows);
+  const uint32_t max_tok = (uint32_t)std::min<uint64_t>(len / 4 + 2, tr->cfg.max_nnz);
+  XF_TRY(tr->ing_text.ensure(len + 16));
+  XF_TRY(tr->ing_row_ptr.ensure(((size_t)max_rows + 2) * 4));
+  XF_TRY(tr->ing_keys.ensure(((size_t)max_tok + 1) * 8));
+  XF_TRY(tr->ing_labels.ensure((size_t)max_rows + 1));
+  XF_TRY(tr->ing_totals.ensure(16));
+  const void* src = text;
+  if (len && !xf_is_pinned(text)) {
+    XF_TRY(tr->ing_stage.ensure(len));
+    memcpy(tr->ing_stage.p, text, len);
+    src = tr->ing_stage.p;
+  }
+  if (len) XF_CUDA_TRY(cudaMemcpyAsync(tr->ing_text.p, src, len, cudaMemcpyHostToDevice, st));
+  // totals = {rows, tokens, parse error}; the parser's error word is its own, not the table's sticky one
+  XF_CUDA_TRY(cudaMemsetAsync(tr->ing_totals.p, 0, 16, st));
+  XF_TRY(xf_launch_parse(tr->ing_text.as<char>(), len, tr->ing_scratch, tr->ing_row_ptr.as<uint32_t>(),
+                         tr->ing_keys.as<uint64_t>(), tr->ing_labels.as<uint8_t>(), max_rows, max_tok,
+                         tr->ing_totals.as<uint32_t>(), tr->ing_totals.as<int>() + 2, st));
+  tr->launches += 5;
+  uint32_t tot[3] = {0, 0, 0};
+  XF_CUDA_TRY(cudaMemcpyAsync(tot, tr->ing_totals.p, 12, cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  const int e = (int)tot[2];
+  tr->ing_rows = tr->ing_nnz = 0;
+  if (e == 4) { xf_set_error("ingest: token without three ':'-separated fields"); return XF_ERR_IO; }
+  if (e == 3 || tot[0] > max_rows || tot[1] > max_tok) {
+    xf_set_error("ingest: block (%u rows, %u tokens) exceeds trainer limits (%u, %u)", tot[0], tot[1],
+                 tr->cfg.max_rows, tr->cfg.max_nnz);
+    return XF_ERR_ARG;
+  }
+  tr->ing_rows = tot[0];
+  tr->ing_nnz = tot[1];
+  *rows = tot[0];
+  *nnz = tot[1];
+  return XF_OK;
+}
+
+static int xf_ingested_range(xf_trainer* tr, uint32_t row_start, uint32_t row_end) {
+  if (!tr) return XF_ERR_ARG;
+  if (row_start > row_end || row_end > tr->ing_rows) { xf_set_error("row range outside the ingested block"); return XF_ERR_ARG; }
+  if (tr->mg && (row_start != 0 || row_end != tr->ing_rows)) {
+    xf_set_error("sharded trainers step whole ingested blocks (core_num = 1)");
+    return XF_ERR_ARG;
+  }
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_step_ingested(xf_trainer* tr, uint32_t row_start, uint32_t row_end) {
+  XF_TRY(xf_ingested_range(tr, row_start, row_end));
+  if (row_end == row_start) return XF_OK;
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const uint32_t rows = row_end - row_start;
+  // row_ptr holds absolute token offsets, so a slice is just a shifted row_ptr / labels pointer; the
+  // per-token scratch (FM: touched[]) is indexed by absolute position and must not keep stale slices
+  if (!tr->table->view.lazy)
+    XF_CUDA_TRY(cudaMemsetAsync(tr->touched.p, 0xFF, (size_t)tr->ing_nnz * 4, tr->table->stream));
+  XF_TRY(xf_step_device_impl(tr, tr->ing_row_ptr.as<uint32_t>() + row_start, tr->ing_keys.as<uint64_t>(),
+                             tr->ing_labels.as<uint8_t>() + row_start, rows, tr->ing_nnz, 0, nullptr));
+  ++tr->n_steps;
+  tr->n_rows += rows;
+  tr->last_rows = rows;
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_ingested_export(xf_trainer* tr, uint32_t* row_ptr_out, uint64_t* keys_out, uint8_t* labels_out) {
+  if (!tr) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
+  if (row_ptr_out)
+    XF_CUDA_TRY(cudaMemcpy(row_ptr_out, tr->ing_row_ptr.p, ((size_t)tr->ing_rows + 1) * 4, cudaMemcpyDeviceToHost));
+  if (keys_out && tr->ing_nnz)
+    XF_CUDA_TRY(cudaMemcpy(keys_out, tr->ing_keys.p, (size_t)tr->ing_nnz * 8, cudaMemcpyDeviceToHost));
+  if (labels_out && tr->ing_rows)
+    XF_CUDA_TRY(cudaMemcpy(labels_out, tr->ing_labels.p, (size_t)tr->ing_rows, cudaMemcpyDeviceToHost));
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_predict_ingested(xf_trainer* tr, uint32_t row_start, uint32_t row_end, float* pctr_out,
+                                       uint8_t* labels_out) {
+  XF_TRY(xf_ingested_range(tr, row_start, row_end));
+  if (row_end == row_start) return XF_OK;
+  if (!pctr_out) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const uint32_t rows = row_end - row_start;
+  cudaStream_t st = tr->table->stream;
+  XF_TRY(xf_step_device_impl(tr, tr->ing_row_ptr.as<uint32_t>() + row_start, tr->ing_keys.as<uint64_t>(),
+                             tr->ing_labels.as<uint8_t>() + row_start, rows, tr->ing_nnz, 1, nullptr));
+  XF_CUDA_TRY(cudaMemcpyAsync(pctr_out, tr->pctr.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+  if (labels_out)
+    XF_CUDA_TRY(cudaMemcpyAsync(labels_out, tr->ing_labels.as<uint8_t>() + row_start, rows, cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  return tr->table->check_error();
 }
 
 XF_DLL int xf_trainer_set_profile(xf_trainer* tr, int on) {

@@ -104,6 +104,10 @@ struct xf_trainer {
   uint64_t host_unique = 0;             // unique keys counted on the host (sharded path)
   uint32_t last_rows = 0;
   uint64_t launches = 0;
+  // device-side ingest (xf_trainer_ingest_text): raw text, parser scratch, the block's CSR
+  XfDevBuf ing_text, ing_scratch, ing_row_ptr, ing_keys, ing_labels, ing_totals;
+  XfPinBuf ing_stage;
+  uint32_t ing_rows = 0, ing_nnz = 0;
   void* mg = nullptr;                   // multi-GPU exchange state (comm.cu)
   cudaEvent_t input_ready = nullptr;    // set by the host-batch paths: H2D of the batch about to be stepped
   // optional per-kernel timing (xf_trainer_set_profile): events around the kernels of each step
@@ -113,6 +117,9 @@ struct xf_trainer {
 };
 
 // ingest.cu
+int xf_launch_parse(const char* d_text, uint64_t len, XfDevBuf& scratch, uint32_t* d_row_ptr, uint64_t* d_keys,
+                    uint8_t* d_labels, uint32_t max_rows, uint32_t max_tok, uint32_t* d_totals, int* d_error,
+                    cudaStream_t st);
 int xf_launch_hash_ids(const uint32_t* d_ids, uint32_t n, uint64_t* d_keys, cudaStream_t st);
 
 // multi-GPU pieces implemented in comm.cu

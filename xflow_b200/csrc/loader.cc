@@ -39,6 +39,7 @@ XF_DLL int xf_hash_decimal_ids(const uint64_t* ids, uint64_t n, uint64_t* out) {
 struct xf_loader {
   FILE* fp = nullptr;
   char* buf = nullptr;
+  bool buf_pinned = false;
   size_t buf_size = 0, bmax = 0, btop = 0;
   // two output sets, alternated by every xf_loader_next: the arrays of block i stay valid (e.g. as
   // the source of an asynchronous H2D copy) while block i+1 is being parsed
@@ -79,7 +80,11 @@ XF_DLL int xf_loader_open(xf_loader** out, const char* path, uint64_t block_byte
   xf_loader* l = new xf_loader;
   l->fp = fp;
   l->buf_size = (size_t)block_bytes;
-  l->buf = (char*)malloc(l->buf_size + 1);
+  {
+    bool pin_text = true;  // the raw block is also what the device parser uploads (xf_loader_next_raw)
+    l->buf = (char*)xf_host_alloc(l->buf_size + 1, &pin_text);
+    l->buf_pinned = pin_text;
+  }
   // shortest legal row "0\ta:b:c\n" = 8 bytes, shortest extra token " a:b:c" = 6 bytes
   l->max_rows = l->buf_size / 2 + 2;
   l->max_tok = l->buf_size / 4 + 2;
@@ -106,7 +111,7 @@ XF_DLL int xf_loader_open(xf_loader** out, const char* path, uint64_t block_byte
 XF_DLL int xf_loader_close(xf_loader* l) {
   if (!l) return XF_OK;
   if (l->fp) fclose(l->fp);
-  free(l->buf);
+  xf_host_free(l->buf, l->buf_pinned);
   for (int s = 0; s < 2; ++s) {
     xf_host_free(l->row_ptr_set[s], l->pinned);
     xf_host_free(l->keys_set[s], l->pinned);
@@ -116,14 +121,9 @@ XF_DLL int xf_loader_close(xf_loader* l) {
   return XF_OK;
 }
 
-XF_DLL int xf_loader_next(xf_loader* l, uint32_t* rows_out, uint32_t* nnz_out) {
-  if (!l || !rows_out || !nnz_out) return XF_ERR_ARG;
+// block formation (load_data_from_disk.cc:108-124): returns the length of the parse region [0, end)
+static size_t xf_loader_form_block(xf_loader* l) {
   char* buf = l->buf;
-  l->cur ^= 1;
-  l->row_ptr = l->row_ptr_set[l->cur];
-  l->keys = l->keys_set[l->cur];
-  l->labels = l->labels_set[l->cur];
-  // --- block formation (load_data_from_disk.cc:108-124)
   if (l->bmax < l->btop) memmove(buf, buf + l->bmax, l->btop - l->bmax);
   l->btop -= l->bmax;
   l->btop += fread(buf + l->btop, 1, l->buf_size - 1 - l->btop, l->fp);
@@ -137,6 +137,25 @@ XF_DLL int xf_loader_next(xf_loader* l, uint32_t* rows_out, uint32_t* nnz_out) {
     end = l->bmax;
   }
   buf[end] = '\0';
+  return end;
+}
+
+XF_DLL int xf_loader_next_raw(xf_loader* l, const char** text, uint64_t* len) {
+  if (!l || !text || !len) return XF_ERR_ARG;
+  const size_t end = xf_loader_form_block(l);
+  *text = l->buf;
+  *len = (uint64_t)end;
+  return XF_OK;
+}
+
+XF_DLL int xf_loader_next(xf_loader* l, uint32_t* rows_out, uint32_t* nnz_out) {
+  if (!l || !rows_out || !nnz_out) return XF_ERR_ARG;
+  char* buf = l->buf;
+  l->cur ^= 1;
+  l->row_ptr = l->row_ptr_set[l->cur];
+  l->keys = l->keys_set[l->cur];
+  l->labels = l->labels_set[l->cur];
+  const size_t end = xf_loader_form_block(l);
 
   // --- parse
   uint32_t rows = 0, nnz = 0;

@@ -155,14 +155,37 @@ void WorkerBase::update(int start, int end) {
   rows_trained += rows;
 }
 
+// a text block of `bytes` bytes holds at most bytes/8 rows ("0\ta:b:c\n") and bytes/6 tokens ("a:b:c ")
+void WorkerBase::ensure_trainer_for_block(uint64_t bytes) {
+  ensure_trainer((uint32_t)(bytes / 8 + 2), (uint32_t)(bytes / 6 + 2));
+}
+
 void WorkerBase::batch_training() {
-  ensure_trainer(1024, 65536);
+  const bool host_parse = env_int("XFLOW_HOST_PARSE", 0) != 0;
+  if (host_parse) ensure_trainer(1024, 65536);
+  else ensure_trainer_for_block((uint64_t)block_size << 20);
   must(xf_trainer_init_push(trainer_), "xf_trainer_init_push");  // lr_worker.cc:180-182
   for (int epoch = 0; epoch < epochs; ++epoch) {
     xf_loader* loader = nullptr;
     must(xf_loader_open(&loader, train_data_path, (uint64_t)block_size << 20), "xf_loader_open");  // :184
     int block = 0;
-    while (true) {
+    while (!host_parse) {
+      // default path: the host only forms the block; parsing, hashing and the step run on the device
+      const char* text = nullptr;
+      uint64_t len = 0;
+      must(xf_loader_next_raw(loader, &text, &len), "xf_loader_next_raw");
+      if (len == 0) break;
+      uint32_t rows = 0, nnz = 0;
+      must(xf_trainer_ingest_text(trainer_, text, len, &rows, &nnz), "xf_trainer_ingest_text");
+      if (rows == 0) break;  // :189
+      const uint32_t thread_size = rows / (uint32_t)core_num;  // :190 — remainder rows are dropped, as in the reference
+      for (uint32_t i = 0; i < (uint32_t)core_num; ++i) {      // :192-196
+        must(xf_trainer_step_ingested(trainer_, i * thread_size, (i + 1) * thread_size), "xf_trainer_step_ingested");
+        rows_trained += thread_size;
+      }
+      ++block;
+    }
+    while (host_parse) {
       // the loader alternates two output sets; before it overwrites one, the copies that read it
       // must have drained
       if (trainer_) must(xf_trainer_wait_uploads(trainer_), "xf_trainer_wait_uploads");
@@ -216,7 +239,35 @@ void WorkerBase::predict(int rank_arg, int block) {
   xf_loader* loader = nullptr;
   must(xf_loader_open(&loader, test_data_path, (uint64_t)test_block_size << 20), "xf_loader_open");
   test_auc_vec.clear();
-  while (true) {
+  const bool host_parse = env_int("XFLOW_HOST_PARSE", 0) != 0;
+  if (!host_parse) ensure_trainer_for_block((uint64_t)test_block_size << 20);
+  std::vector<float> pctr_buf;
+  std::vector<uint8_t> label_buf;
+  while (!host_parse) {
+    const char* text = nullptr;
+    uint64_t len = 0;
+    must(xf_loader_next_raw(loader, &text, &len), "xf_loader_next_raw");
+    if (len == 0) break;
+    uint32_t rows = 0, nnz = 0;
+    must(xf_trainer_ingest_text(trainer_, text, len, &rows, &nnz), "xf_trainer_ingest_text");
+    if (rows == 0) break;
+    const uint32_t thread_size = rows / (uint32_t)core_num;
+    pctr_buf.resize(thread_size);
+    label_buf.resize(thread_size);
+    for (uint32_t i = 0; i < (uint32_t)core_num; ++i) {
+      must(xf_trainer_predict_ingested(trainer_, i * thread_size, (i + 1) * thread_size, pctr_buf.data(),
+                                       label_buf.data()),
+           "xf_trainer_predict_ingested");
+      for (uint32_t r = 0; r < thread_size; ++r) {
+        auc_key ak;
+        ak.label = label_buf[r];
+        ak.pctr = pctr_buf[r];
+        test_auc_vec.push_back(ak);
+        md << pctr_buf[r] << "\t" << 1 - ak.label << "\t" << ak.label << std::endl;  // lr_worker.cc:67
+      }
+    }
+  }
+  while (host_parse) {
     uint32_t rows = 0, nnz = 0;
     must(xf_loader_next(loader, &rows, &nnz), "xf_loader_next");
     if (rows == 0) break;
