@@ -193,6 +193,45 @@ def run_reference_arm(args, wl):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def text_leg(api, tr, wl, B, passes=12, warm=2):
+    """File -> model throughput: a text shard of one batch (page-cache warm), every pass = block read +
+    H2D of the raw text + device parse/hash + one training step.  Host wall clock around synced passes."""
+    import ctypes as C
+    from xflow_b200 import datagen
+    tmp = tempfile.mkdtemp(prefix="xftext_")
+    path = os.path.join(tmp, "shard-00000")
+    rp, ids, lab = datagen.make_ids(seed=777, rows=B, nnz_per_row=wl["nnz"], id_space=wl["id_space"],
+                                    dist=wl["dist"], zipf_s=1.05)
+    datagen.write_text(path, rp, ids, lab)
+    size = os.path.getsize(path)
+    lib = api.lib()
+    text, ln, r, z = C.c_void_p(), C.c_uint64(), C.c_uint32(), C.c_uint32()
+    times = []
+    for p in range(warm + passes):
+        ld = api.Loader(path, size + (1 << 20))
+        tr.sync()
+        t0 = time.perf_counter()
+        rows = 0
+        while True:
+            assert lib.xf_loader_next_raw(ld.h, C.byref(text), C.byref(ln)) == 0
+            if not ln.value:
+                break
+            assert lib.xf_trainer_ingest_text(tr.h, text, ln.value, C.byref(r), C.byref(z)) == 0, lib.xf_last_error()
+            assert lib.xf_trainer_step_ingested(tr.h, 0, r.value) == 0, lib.xf_last_error()
+            rows += r.value
+        tr.sync()
+        if p >= warm:
+            times.append(time.perf_counter() - t0)
+        assert rows == B
+        ld.close()
+    os.remove(path)
+    t = float(np.mean(times))
+    return {"value": B / t, "unit": "examples/s", "ms_per_step": t * 1e3, "text_bytes_per_step": size,
+            "text_gbs": size / t / 1e9, "passes": passes,
+            "api": "xf_loader_next_raw + xf_trainer_ingest_text + xf_trainer_step_ingested (C ABI): block read "
+                   "from the page cache, H2D of raw text, parse + hash + step on the device"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +240,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lr_ftrl", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-text-e2e", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.warmup = max(args.warmup, 3)
@@ -312,6 +352,11 @@ def main():
             return f0.elapsed_time(f1)
         ms_e2e_keys = e2e_leg(False)
         ms_e2e = e2e_leg(True)
+        # ---------------- file -> model (reported separately): one batch as a text shard in the
+        # reference's format, read by xf_loader_next_raw, parsed + hashed + trained on the device
+        text_e2e = None
+        if world == 1 and not args.no_text_e2e:
+            text_e2e = text_leg(api, tr, wl, B)
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
@@ -386,6 +431,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
+        if text_e2e:
+            line["e2e_text"] = text_e2e
         if world == 1 and not args.no_cpu_baseline:
             try:
                 rows = 16384

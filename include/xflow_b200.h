@@ -115,6 +115,9 @@ XF_DLL int xf_table_list_keys(xf_table* t, uint64_t* keys_out, uint64_t max_keys
 /* binary checkpoint of the whole shard (keys + full optimizer state) */
 XF_DLL int xf_table_save(xf_table* t, const char* path);
 XF_DLL int xf_table_load(xf_table* t, const char* path);
+/* text model dump, one "<key>\t<w>[\t<v_0> ... <v_K-1>]" line per key in key order (weights only, %.9g);
+ * nonzero_only skips keys whose weights are all exactly 0 (FTRL's L1 zeros).  *written = lines (may be NULL) */
+XF_DLL int xf_table_dump_text(xf_table* t, const char* path, int nonzero_only, uint64_t* written);
 /* use an external CUDA stream (cudaStream_t passed as void*) for all table work; NULL = own stream */
 XF_DLL int xf_table_set_stream(xf_table* t, void* cuda_stream);
 XF_DLL int xf_table_sync(xf_table* t);
@@ -206,6 +209,9 @@ XF_DLL int xf_host_free(void* p);
 /* Base::calculate_auc (base.h:84-110), host: out[0]=logloss (base-2, not negated, float accumulator)
  * out[1]=auc (float `area`; NaN when single-class) out[2]=tp out[3]=fp */
 XF_DLL int xf_auc_logloss(const int32_t* labels, const float* pctr, uint64_t n, double out[4]);
+/* the same metric in exact arithmetic (not the reference's numbers): out[0] = mean negative natural-log
+ * likelihood, out[1] = AUC with ties counted 1/2, out[2]=positives out[3]=negatives */
+XF_DLL int xf_auc_logloss_exact(const int32_t* labels, const float* pctr, uint64_t n, double out[4]);
 
 /* ------------------------------------------------------------------------------------------------
  * 4. Host ingest

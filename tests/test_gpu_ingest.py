@@ -170,3 +170,33 @@ def test_cli_device_ingest_equals_host_parse(tmp_path):
         outs.append(((d / "pred_0_0.txt").read_text(), [l for l in r.stdout.splitlines() if "logloss" in l]))
     assert outs[0][0] == outs[1][0]
     assert outs[0][1] == outs[1][1]
+
+
+@pytest.mark.parametrize("K", [0, 3])
+def test_text_model_dump(tmp_path, K):
+    """xf_table_dump_text: key-ordered "<key>\\t<w>[\\t<v...>]" lines that round-trip floats."""
+    rng = np.random.default_rng(9)
+    n = 1000
+    keys = np.unique(rng.integers(1, 1 << 63, n, dtype=np.uint64))
+    n = keys.size
+    w = rng.standard_normal(n).astype(np.float32)
+    w[::3] = 0.0
+    v = rng.standard_normal((n, K)).astype(np.float32) if K else None
+    if K:
+        v[::3] = 0.0
+        v[3::6] = 0.0   # some rows with w != 0 but v == 0
+    t = api.Table(latent_dim=K, capacity=1 << 12)
+    z = np.zeros(n, np.float32)
+    t.import_(keys, w=w, nw=z, zw=z, v=v, nv=None if v is None else np.zeros_like(v), zv=None if v is None else np.zeros_like(v))
+    for nonzero_only in (False, True):
+        path = str(tmp_path / ("m%d.txt" % nonzero_only))
+        lines = t.dump_text(path, nonzero_only=nonzero_only)
+        got = [l.rstrip("\n").split("\t") for l in open(path)]
+        assert lines == len(got)
+        keep = np.ones(n, bool) if not nonzero_only else ((w != 0) | (v != 0).any(axis=1) if K else (w != 0))
+        assert [int(g[0]) for g in got] == [int(k) for k in keys[keep]]        # key order
+        assert np.array_equal(np.array([g[1] for g in got], np.float32), w[keep])
+        if K:
+            gv = np.array([[float(x) for x in g[2].split(" ")] for g in got], np.float32)
+            assert np.array_equal(gv, v[keep])
+    t.close()

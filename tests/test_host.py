@@ -109,3 +109,42 @@ def test_auc_logloss_matches_oracle():
         assert a["tp"] == b["tp"] and a["fp"] == b["fp"]
         assert a["logloss"] == b["logloss"]
         assert (np.isnan(a["auc"]) and np.isnan(b["auc"])) or a["auc"] == b["auc"]
+
+
+def test_exact_metric_matches_sklearn():
+    """xf_auc_logloss_exact: tie-aware AUC and natural-log logloss in exact arithmetic."""
+    from sklearn.metrics import log_loss, roc_auc_score
+    rng = np.random.default_rng(3)
+    n = 20000
+    y = (rng.random(n) < 0.3).astype(np.int32)
+    p = np.clip(np.round(rng.random(n) * 0.6 + y * 0.2, 2), 0.01, 0.99).astype(np.float32)  # many ties
+    m = api.auc_logloss_exact(y, p)
+    assert m["positives"] == int(y.sum()) and m["negatives"] == int(n - y.sum())
+    assert abs(m["auc"] - roc_auc_score(y, p)) < 1e-12
+    assert abs(m["logloss"] - log_loss(y, p.astype(np.float64))) < 1e-9
+    # single-class input has no AUC
+    assert np.isnan(api.auc_logloss_exact(np.ones(5, np.int32), np.full(5, 0.5, np.float32))["auc"])
+    # and the reference-faithful metric is a different quantity: base-2, not negated
+    ref = api.auc_logloss(y, p)
+    assert abs(ref["logloss"] * np.log(2) + m["logloss"]) < 1e-3
+
+
+def test_loader_large_blocks_read_in_parallel_pieces(tmp_path):
+    """Blocks of several MiB are filled by a few pread threads; the rows must not depend on that."""
+    from xflow_b200 import datagen
+    rp, ids, lab = datagen.make_ids(5, 30000, 30, 1 << 40, ragged=True)
+    path = str(tmp_path / "big-00000")
+    datagen.write_text(path, rp, ids, lab)
+    assert os.path.getsize(path) > (8 << 20)
+    def all_rows(block):
+        ks, ys, lens = [], [], []
+        for r, k, y in api.Loader(path, block):
+            ks.append(k); ys.append(y); lens.append(np.diff(r))
+        return np.concatenate(ks), np.concatenate(ys), np.concatenate(lens)
+    small = all_rows(1 << 20)          # single-threaded reads
+    for block in (5 << 20, 64 << 20):  # multi-threaded, with and without a carried tail
+        big = all_rows(block)
+        for a, b in zip(small, big):
+            assert np.array_equal(a, b)
+    assert np.array_equal(small[0], api.hash_decimal_ids(ids))
+    assert np.array_equal(small[1], lab)

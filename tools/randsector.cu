@@ -48,6 +48,73 @@ __global__ void k_rand(uint8_t* base, uint64_t nsect_mask, uint64_t per_thread, 
   if (acc == 0x123456789ull) *sink = acc;
 }
 
+// Ordered variants: what does address ORDER buy?  ORDER 1 = sorted sparse: access number n goes to sector
+// n*S + (hash(n) mod S) — ascending addresses, one touched sector in every S (what a full sort of the
+// batch by table slot would produce).  ORDER 2 = windowed: accesses are random inside a window of W
+// sectors that advances with n (what a one-pass bucketing of the batch by slot prefix would produce).
+template <int MLP, int MODE, int ORDER>
+__global__ void k_ord(uint8_t* base, uint64_t nsect, uint64_t per_thread, uint64_t S, uint64_t W, uint64_t seed,
+                      uint64_t* sink) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t threads = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t total = per_thread * threads;
+  uint64_t acc = 0;
+  for (uint64_t i = 0; i < per_thread; i += MLP) {
+    uint64_t a[MLP], b[MLP], c[MLP], d[MLP];
+    uint8_t* p[MLP];
+#pragma unroll
+    for (int m = 0; m < MLP; ++m) {
+      const uint64_t n = (i + m) * threads + tid;  // all threads sweep the table together
+      uint64_t sect;
+      if (ORDER == 1) sect = n * S + mix(seed + n) % S;
+      else sect = (n * (nsect - W) / total) + mix(seed + n) % W;
+      p[m] = base + ((sect % nsect) << 5);
+    }
+    if (MODE == 2) {
+#pragma unroll
+      for (int m = 0; m < MLP; ++m) atomicAdd(reinterpret_cast<double*>(p[m] + 24), 1.0);
+    } else {
+#pragma unroll
+      for (int m = 0; m < MLP; ++m) ld256(p[m], a[m], b[m], c[m], d[m]);
+#pragma unroll
+      for (int m = 0; m < MLP; ++m) {
+        acc += a[m] ^ b[m] ^ c[m] ^ d[m];
+        if (MODE == 1) st256(p[m], a[m] + 1, b[m], c[m], d[m]);
+      }
+    }
+  }
+  if (acc == 0x123456789ull) *sink = acc;
+}
+
+template <int MLP, int MODE, int ORDER>
+static void run_ord(const char* name, uint8_t* base, uint64_t nsect, uint64_t total, uint64_t S, uint64_t W,
+                    uint64_t* sink) {
+  const int block = 256, grid = 148 * 8;
+  uint64_t threads = (uint64_t)block * grid;
+  uint64_t per_thread = (total / threads / MLP) * MLP;
+  if (per_thread == 0) per_thread = MLP;
+  if (ORDER == 1) S = nsect / (per_thread * threads);  // spread the accesses over the whole table
+  if (S == 0) S = 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_ord<MLP, MODE, ORDER><<<grid, block>>>(base, nsect, per_thread, S, W, 1, sink);
+  float best = 1e30f;
+  for (int r = 0; r < 3; ++r) {
+    cudaEventRecord(e0);
+    k_ord<MLP, MODE, ORDER><<<grid, block>>>(base, nsect, per_thread, S, W, 77 + r, sink);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  double n = (double)per_thread * threads;
+  double gs = n / (best * 1e-3) / 1e9;
+  printf("  %-44s S=%-3llu W=%-8llu %8.2f G sectors/s  %8.1f GB/s%s\n", name, (unsigned long long)S,
+         (unsigned long long)W, gs, gs * 32 * (MODE == 1 ? 2 : 1), MODE == 1 ? " (read+write)" : "");
+}
+
 template <int MLP, int MODE>
 static void run(const char* name, uint8_t* base, uint64_t nsect, uint64_t total, uint64_t* sink) {
   const int block = 256, grid = 148 * 8;
@@ -96,6 +163,20 @@ int main(int argc, char** argv) {
     run<8, 0>("random 32B read, 8 in flight/thread", base, nsect, total, sink);
     run<4, 1>("random 32B read-modify-write, 4", base, nsect, total, sink);
     run<4, 2>("random f64 atomicAdd (RED), 4", base, nsect, total, sink);
+  }
+  // address-order experiments at the default granularity: `total` accesses spread over the table
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  printf("ordered access, table %llu MB, %llu M accesses\n", (unsigned long long)(nsect * 32 >> 20),
+         (unsigned long long)(total / 1000000));
+  run_ord<4, 0, 1>("sorted sparse read", base, nsect, total, 0, 0, sink);
+  run_ord<4, 1, 1>("sorted sparse read-modify-write", base, nsect, total, 0, 0, sink);
+  run_ord<4, 2, 1>("sorted sparse f64 atomicAdd", base, nsect, total, 0, 0, sink);
+  for (uint64_t wmb = 1; wmb <= 256; wmb *= 4) {
+    const uint64_t W = wmb * 1048576ull / 32;
+    if (W >= nsect) break;
+    run_ord<4, 0, 2>("windowed random read", base, nsect, total, 0, W, sink);
+    run_ord<4, 1, 2>("windowed random read-modify-write", base, nsect, total, 0, W, sink);
+    run_ord<4, 2, 2>("windowed random f64 atomicAdd", base, nsect, total, 0, W, sink);
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }

@@ -73,6 +73,8 @@ SIGNATURES = {
     "xf_trainer_step_host_async": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "xf_trainer_step_host_ids_async": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "xf_hash_decimal_ids_device": (_i, [_vp, _u64, _vp, _vp]),
+    "xf_auc_logloss_exact": (_i, [_vp, _vp, _u64, _vp]),
+    "xf_table_dump_text": (_i, [_vp, C.c_char_p, _i, _vp]),
     "xf_trainer_ingest_text": (_i, [_vp, _vp, _u64, _vp, _vp]),
     "xf_trainer_step_ingested": (_i, [_vp, _u32, _u32]),
     "xf_trainer_ingested_export": (_i, [_vp, _vp, _vp, _vp]),
@@ -154,6 +156,15 @@ def auc_logloss(labels, pctr):
     out = np.zeros(4, np.float64)
     _check(lib().xf_auc_logloss(_p(labels), _p(pctr), labels.size, _p(out)))
     return dict(logloss=float(out[0]), auc=float(out[1]), tp=int(out[2]), fp=int(out[3]))
+
+
+def auc_logloss_exact(labels, pctr):
+    """Exact-arithmetic test metric: natural-log logloss (negated) and tie-aware AUC."""
+    labels = np.ascontiguousarray(labels, np.int32)
+    pctr = np.ascontiguousarray(pctr, np.float32)
+    out = np.zeros(4, np.float64)
+    _check(lib().xf_auc_logloss_exact(_p(labels), _p(pctr), labels.size, _p(out)))
+    return dict(logloss=float(out[0]), auc=float(out[1]), positives=int(out[2]), negatives=int(out[3]))
 
 
 class Loader:
@@ -277,6 +288,11 @@ class Table:
 
     def save(self, path):
         _check(lib().xf_table_save(self.h, path.encode()))
+
+    def dump_text(self, path, nonzero_only=False):
+        n = C.c_uint64()
+        _check(lib().xf_table_dump_text(self.h, path.encode(), int(nonzero_only), C.byref(n)))
+        return n.value
 
     def load(self, path):
         _check(lib().xf_table_load(self.h, path.encode()))

@@ -495,6 +495,41 @@ XF_DLL int xf_table_save(xf_table* t, const char* path) {
   return XF_OK;
 }
 
+// text model dump (the reference has none): one line per key, sorted by key,
+//   <key>\t<w>[\t<v_0> ... <v_{K-1}>]      weights only, %.9g (round-trips a float)
+// nonzero_only drops keys whose w (and every v) is exactly 0 — what FTRL's L1 leaves behind.
+XF_DLL int xf_table_dump_text(xf_table* t, const char* path, int nonzero_only, uint64_t* written) {
+  if (!t || !path) return XF_ERR_ARG;
+  uint64_t n = 0;
+  XF_TRY(xf_table_size(t, &n));
+  std::vector<uint64_t> keys(n ? n : 1);
+  uint64_t got = 0;
+  XF_TRY(xf_table_list_keys(t, keys.data(), n, &got));
+  n = std::min(n, got);
+  std::sort(keys.begin(), keys.begin() + n);
+  const size_t K = (size_t)t->view.K;
+  std::vector<float> w(n), v(n * K);
+  XF_TRY(xf_table_export(t, keys.data(), n, w.data(), nullptr, nullptr, K ? v.data() : nullptr, nullptr, nullptr,
+                         nullptr));
+  FILE* f = fopen(path, "w");
+  if (!f) { xf_set_error("cannot open %s for writing", path); return XF_ERR_IO; }
+  uint64_t lines = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (nonzero_only) {
+      bool any = w[i] != 0.0f;
+      for (size_t k = 0; k < K && !any; ++k) any = v[i * K + k] != 0.0f;
+      if (!any) continue;
+    }
+    fprintf(f, "%llu\t%.9g", (unsigned long long)keys[i], (double)w[i]);
+    for (size_t k = 0; k < K; ++k) fprintf(f, "%c%.9g", k ? ' ' : '\t', (double)v[i * K + k]);
+    fputc('\n', f);
+    ++lines;
+  }
+  if (fclose(f) != 0) { xf_set_error("write to %s failed", path); return XF_ERR_IO; }
+  if (written) *written = lines;
+  return XF_OK;
+}
+
 XF_DLL int xf_table_load(xf_table* t, const char* path) {
   if (!t || !path) return XF_ERR_ARG;
   FILE* f = fopen(path, "rb");

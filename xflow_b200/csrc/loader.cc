@@ -14,6 +14,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
 
 #include "../../include/xflow_b200.h"
 #include "hash.h"
@@ -38,6 +44,7 @@ XF_DLL int xf_hash_decimal_ids(const uint64_t* ids, uint64_t n, uint64_t* out) {
 
 struct xf_loader {
   FILE* fp = nullptr;
+  uint64_t file_size = 0, file_pos = 0;  // reads go through pread on fileno(fp)
   char* buf = nullptr;
   bool buf_pinned = false;
   size_t buf_size = 0, bmax = 0, btop = 0;
@@ -79,6 +86,10 @@ XF_DLL int xf_loader_open(xf_loader** out, const char* path, uint64_t block_byte
   }
   xf_loader* l = new xf_loader;
   l->fp = fp;
+  {
+    struct stat sb;
+    l->file_size = (fstat(fileno(fp), &sb) == 0) ? (uint64_t)sb.st_size : 0;
+  }
   l->buf_size = (size_t)block_bytes;
   {
     bool pin_text = true;  // the raw block is also what the device parser uploads (xf_loader_next_raw)
@@ -121,12 +132,50 @@ XF_DLL int xf_loader_close(xf_loader* l) {
   return XF_OK;
 }
 
+// fread replacement: fills dst with up to n bytes from the current file position.  Large requests are
+// split across a few threads (pread at disjoint offsets): one core copies out of the page cache at
+// ~4 GB/s, which would otherwise cap file -> device throughput now that parsing runs on the GPU.
+static size_t xf_read_block(xf_loader* l, char* dst, size_t n) {
+  const int fd = fileno(l->fp);
+  const uint64_t remaining = l->file_size > l->file_pos ? l->file_size - l->file_pos : 0;
+  if (n > remaining) n = (size_t)remaining;
+  if (n == 0) return 0;
+  const size_t kMinPerThread = (size_t)2 << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nthreads = std::min<size_t>(std::min<size_t>(8, hw ? hw : 1), n / kMinPerThread);
+  if (nthreads < 1) nthreads = 1;
+  std::vector<size_t> got(nthreads, 0);
+  auto work = [&](size_t t) {
+    const size_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+    size_t done = 0;
+    while (lo + done < hi) {
+      const ssize_t r = pread(fd, dst + lo + done, hi - lo - done, (off_t)(l->file_pos + lo + done));
+      if (r <= 0) break;
+      done += (size_t)r;
+    }
+    got[t] = done;
+  };
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  // bytes are valid up to the first short piece
+  size_t total = 0;
+  for (size_t t = 0; t < nthreads; ++t) {
+    const size_t want = n * (t + 1) / nthreads - n * t / nthreads;
+    total += got[t];
+    if (got[t] < want) break;
+  }
+  l->file_pos += total;
+  return total;
+}
+
 // block formation (load_data_from_disk.cc:108-124): returns the length of the parse region [0, end)
 static size_t xf_loader_form_block(xf_loader* l) {
   char* buf = l->buf;
   if (l->bmax < l->btop) memmove(buf, buf + l->bmax, l->btop - l->bmax);
   l->btop -= l->bmax;
-  l->btop += fread(buf + l->btop, 1, l->buf_size - 1 - l->btop, l->fp);
+  l->btop += xf_read_block(l, buf + l->btop, l->buf_size - 1 - l->btop);
   l->bmax = l->btop;
   size_t end;
   if (l->btop + 1 == l->buf_size) {

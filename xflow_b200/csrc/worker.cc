@@ -298,6 +298,13 @@ void WorkerBase::predict(int rank_arg, int block) {
   } else {
     std::cout << "auc = " << (float)m[1] << "\ttp = " << (int)m[2] << " fp = " << (size_t)m[3] << std::endl;
   }
+  if (env_int("XFLOW_EXACT_METRIC", 0)) {
+    // the same test set in exact arithmetic (natural-log logloss, tie-aware AUC); off by default so that
+    // stdout stays the reference's
+    double x[4] = {0, 0, 0, 0};
+    xf_auc_logloss_exact(labels.data(), pctr.data(), labels.size(), x);
+    std::cout << "exact: logloss(ln) = " << x[0] << "\tauc = " << x[1] << std::endl;
+  }
 }
 
 void WorkerBase::train() {
