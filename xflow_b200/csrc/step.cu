@@ -28,9 +28,10 @@
 
 template <int VEC>
 __device__ __forceinline__ void xf_ldv_step(const float* p, float (&o)[VEC]) {
-  if (VEC == 4) { float4 t = __ldcg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1 % VEC] = t.y; o[2 % VEC] = t.z; o[3 % VEC] = t.w; }
-  else if (VEC == 2) { float2 t = __ldcg(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1 % VEC] = t.y; }
-  else { o[0] = __ldcg(p); }
+  // through L1: v does not change during the step kernel (see xf_load_head_l1), hot rows stay SM-local
+  if (VEC == 4) { float4 t = __ldca(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1 % VEC] = t.y; o[2 % VEC] = t.z; o[3 % VEC] = t.w; }
+  else if (VEC == 2) { float2 t = __ldca(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1 % VEC] = t.y; }
+  else { o[0] = __ldca(p); }
 }
 // vector reduction (no return value) into global memory: one L2 atomic transaction per 8 / 16 bytes
 template <int VEC>
@@ -77,7 +78,7 @@ __device__ __forceinline__ void xf_fm_token_grad(const XfTableView& t, uint32_t 
   uint8_t* rowp = xf_row(t, slot);
   const float* vp = xf_row_v(rowp);
   float* gvp = xf_row_gv(rowp, K);
-  const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
+  const uint32_t flags = __ldca(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
   const bool ready = (flags & XF_FLAG_V_READY) != 0;
   for (int k = 0; k < K; k += VEC) {
     float v[VEC], gc[VEC];
@@ -100,7 +101,7 @@ __device__ __forceinline__ void xf_fm_token_grad_smem(const XfTableView& t, uint
   const int K = t.K;
   const uint8_t* rowp = xf_row(t, slot);
   const float* vp = reinterpret_cast<const float*>(rowp + 32);
-  const uint32_t flags = __ldcg(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
+  const uint32_t flags = __ldca(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
   const bool ready = (flags & XF_FLAG_V_READY) != 0;
   for (int k = 0; k < K; k += VEC) {
     float v[VEC];
@@ -169,8 +170,8 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
       const uint64_t p0 = xf_slot_hash(k0, t.log2cap), p1 = xf_slot_hash(k1, t.log2cap);
       XfHead h0, h1;
       h0.key = h1.key = XF_EMPTY_KEY;
-      if (v0) h0 = xf_load_head(xf_row(t, p0));
-      if (v1) h1 = xf_load_head(xf_row(t, p1));
+      if (v0) h0 = FM ? xf_load_head_l1(xf_row(t, p0)) : xf_load_head(xf_row(t, p0));
+      if (v1) h1 = FM ? xf_load_head_l1(xf_row(t, p1)) : xf_load_head(xf_row(t, p1));
       uint32_t s0 = XF_NO_SLOT, s1 = XF_NO_SLOT;
       if (v0) {
         const int64_t r = xf_probe_from<true>(t, k0, p0, h0);

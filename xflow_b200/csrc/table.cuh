@@ -133,6 +133,25 @@ __device__ __forceinline__ XfHead xf_load_head(const uint8_t* row) {
   return h;
 }
 
+// Same sector through L1 (ld.global.ca).  Only for kernels in which w / n / z / flags of existing rows do
+// not change while the kernel runs (the eager step: it adds to g / gv with L2 atomics and inserts keys,
+// nothing else).  A stale copy can then differ from L2 only by showing EMPTY for a slot that was claimed
+// during this kernel — the insert CAS resolves that (xf_probe_from), and a row inserted during the kernel
+// still has its default parameters.  With skewed ids this keeps each SM's reads of the hot rows local:
+// through L2 every token of the hottest key queues on one slice (measured).
+__device__ __forceinline__ XfHead xf_load_head_l1(const uint8_t* row) {
+  uint64_t q0, q1, q2, q3;
+  asm volatile("ld.global.ca.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(row));
+  XfHead h;
+  h.key = q0;
+  h.w = __uint_as_float((uint32_t)q1);
+  h.n = __uint_as_float((uint32_t)(q1 >> 32));
+  h.z = __uint_as_float((uint32_t)q2);
+  h.flags = (uint32_t)(q2 >> 32);
+  h.g = __longlong_as_double((long long)q3);
+  return h;
+}
+
 // full-sector store of the head (one 256-bit STG: no partial-sector write, no read-for-fill)
 __device__ __forceinline__ void xf_store_head(uint8_t* row, const XfHead& h) {
   const uint64_t q1 = (uint64_t)__float_as_uint(h.w) | ((uint64_t)__float_as_uint(h.n) << 32);
