@@ -53,10 +53,12 @@ __device__ __forceinline__ void xf_stv(float* p, const float (&o)[VEC]) {
 // -------------------------------------------------------------------------------------------------
 // optimizer step over a list of rows
 // -------------------------------------------------------------------------------------------------
-// TPS (power of two <= 32) consecutive lanes own one row: lane q handles latent coordinates
-// [q*VEC, q*VEC+VEC) and lane 0 additionally the scalar w coordinate.
+// A warp takes 32 consecutive entries of the row list (one coalesced load), compacts the live ones with a
+// ballot (the fused step's touched[] is mostly empty: one entry per TOKEN, one live entry per KEY) and
+// hands them out to groups of TPS (power of two <= 32) consecutive lanes: lane q of a group handles
+// latent coordinates [q*VEC, q*VEC+VEC) and lane 0 additionally the scalar w coordinate.
 //   SLOTG = true : gradients are the row's own accumulators (fused step).  g <- g / rows, then the
-//                  accumulators are reset (g = -0.0f marker, gv = 0).
+//                  accumulators are reset (g = -0.0 marker, L = Aq = 0).
 //   SLOTG = false: gradients come from gw[i] / gv[i*K+k] (Push).  part bit0: apply w, bit1: apply v.
 template <int VEC, bool SLOTG>
 __global__ void __launch_bounds__(256)
@@ -68,94 +70,114 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
   __syncthreads();
   unsigned int live_acc = 0;
   const int K = t.K;
-  const uint64_t gthread = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
-  const int q = (int)(threadIdx.x & (unsigned)(tps - 1));
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned group_mask = (tps == 32) ? 0xffffffffu : (((1u << tps) - 1u) << (lane & ~(unsigned)(tps - 1)));
-  const uint64_t n_round = (n * (uint64_t)tps + nthreads - 1) / nthreads * nthreads;  // keep groups converged
+  const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const int q = (int)(lane & (unsigned)(tps - 1));
+  const int gi = (int)(lane / (unsigned)tps);  // which group of the warp
+  const int ngroups = 32 / tps;
+  const int leader = (int)(lane & ~(unsigned)(tps - 1));
+  const unsigned group_mask = (tps == 32) ? 0xffffffffu : (((1u << tps) - 1u) << leader);
+  const int nchunk = K / VEC;
 
-  for (uint64_t x = gthread; x < n_round; x += nthreads) {
-    const uint64_t i_fwd = x / (uint64_t)tps;
-    const bool live = i_fwd < n;
+  for (uint64_t base = gwarp * 32; base < n; base += nwarps * 32) {
     // Fused step: walk the touched array BACKWARDS.  The rows touched last by the step kernel are
     // the ones still resident (dirty) in L2; a forward walk meets them only after they have been
     // evicted (LRU thrash: ncu showed 44 % L2 hits forward).
-    const uint64_t i = (SLOTG && live) ? (n - 1 - i_fwd) : i_fwd;
-    uint8_t* rowp = nullptr;
-    if (live) {
-      const uint32_t s = __ldcs(slots + i);
-      if (s != 0xFFFFFFFFu) rowp = xf_row(t, s);
-    }
-    // the group leader reads the head sector once (one 256-bit load) and shares key / flags
-    XfHead h;
-    h.key = 0; h.flags = 0; h.w = h.n = h.z = 0.f; h.g = 0.0;
-    if (q == 0 && rowp != nullptr) h = xf_load_head(rowp);
-    const int leader = (int)(lane & ~(unsigned)(tps - 1));
-    const uint64_t key = __shfl_sync(group_mask, (unsigned long long)h.key, leader);
-    const uint32_t flags = __shfl_sync(group_mask, h.flags, leader);
-    if (live_total != nullptr) {
-      // rows actually updated (= unique keys of the batch in the fused step): count per warp
-      const unsigned lm = __ballot_sync(0xffffffffu, q == 0 && rowp != nullptr);
-      if (lane == 0) live_acc += __popc(lm);
-    }
-    if (rowp == nullptr) continue;
+    const uint64_t e_fwd = base + lane;
+    const uint64_t e_i = (SLOTG && e_fwd < n) ? (n - 1 - e_fwd) : e_fwd;
+    const uint32_t s_lane = (e_fwd < n) ? __ldcs(slots + e_i) : 0xFFFFFFFFu;
+    unsigned pend = __ballot_sync(0xffffffffu, s_lane != 0xFFFFFFFFu);
+    // rows actually updated (= unique keys of the batch in the fused step)
+    if (live_total != nullptr && lane == 0) live_acc += __popc(pend);
 
-    if (q == 0) {
-      if (!SLOTG) xf_apply_pending(t, h);  // lazy tables: fold the pending batch step in first
-      if (part & 1) {
-        // the accumulated sum is rounded to float once (push_gradient is a float vector), then / rows
-        const float g = SLOTG ? xf_div_rows((float)h.g, rows) : gw[i];
-        xf_opt_coord(t, g, h.w, h.n, h.z);
+    while (pend) {
+      // group gi takes the gi-th live entry of this round
+      const int cnt = __popc(pend);
+      const unsigned src = (gi < cnt) ? __fns(pend, 0, gi + 1) : 0u;
+      const uint32_t s = __shfl_sync(0xffffffffu, s_lane, (int)src);
+      const uint64_t i = __shfl_sync(0xffffffffu, (unsigned long long)e_i, (int)src);
+      uint8_t* rowp = (gi < cnt) ? xf_row(t, s) : nullptr;
+      pend = (cnt <= ngroups) ? 0u : (pend & ~((2u << __fns(pend, 0, ngroups)) - 1u));
+
+      // Every load of the row is issued before anything is consumed: slot -> {head, accumulators, v, nv,
+      // zv} is then two DRAM latencies deep (measured: the dependent chain head -> v -> nv/zv cost 3.5x).
+      // The latent loads are speculative: a row whose latent block is not materialised ignores them.
+      const bool lat = K > 0 && (part & 2) && rowp != nullptr;
+      float* vp = lat ? xf_row_v(rowp) : nullptr;
+      float* nvp = lat ? xf_row_nv(rowp, K) : nullptr;
+      float* zvp = lat ? xf_row_zv(rowp, K) : nullptr;
+      float v0[VEC], n0[VEC], z0[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { v0[e] = 0.f; n0[e] = 0.f; z0[e] = 0.f; }
+      const bool has0 = lat && q < nchunk;
+      if (has0) {
+        xf_ldv<VEC>(vp + q * VEC, v0);
+        if (t.opt == XF_OPT_FTRL) { xf_ldv<VEC>(nvp + q * VEC, n0); xf_ldv<VEC>(zvp + q * VEC, z0); }
       }
-      if (SLOTG) h.g = -0.0;  // "untouched" marker for the next batch
-      if (K > 0 && (part & 2)) h.flags |= XF_FLAG_V_READY;
-      xf_store_head(rowp, h);  // one full-sector store
-    }
-    if (K > 0 && (part & 2)) {
-      const bool ready = (flags & XF_FLAG_V_READY) != 0;
-      float* vp = xf_row_v(rowp);
-      float* gvp = xf_row_gv(rowp, K);
-      float* nvp = xf_row_nv(rowp, K);
-      float* zvp = xf_row_zv(rowp, K);
-      const int nchunk = K / VEC;
-      for (int c = q; c < nchunk; c += tps) {
-        const int k = c * VEC;
-        float v[VEC], g[VEC], nn[VEC], zz[VEC];
-        if (ready) {
-          xf_ldv<VEC>(vp + k, v);
-        } else {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) v[e] = xf_v_init(t, key, (uint32_t)(k + e));
+      // fused step: gv[k] = Aq - v[k] * L (table.cuh); every lane of the group reads the same 16 bytes
+      double accL = 0.0, accA = 0.0;
+      if (SLOTG && has0) {
+        const double2 a = __ldcg(reinterpret_cast<const double2*>(xf_row_acc(rowp, K)));
+        accL = a.x;
+        accA = a.y;
+      }
+      // the group leader reads the head sector once (one 256-bit load) and shares key / flags
+      XfHead h;
+      h.key = 0; h.flags = 0; h.w = h.n = h.z = 0.f; h.g = 0.0;
+      if (q == 0 && rowp != nullptr) h = xf_load_head(rowp);
+      const uint64_t key = __shfl_sync(group_mask, (unsigned long long)h.key, leader);
+      const uint32_t flags = __shfl_sync(group_mask, h.flags, leader);
+      if (rowp == nullptr) continue;  // whole group (pend is warp-uniform, so the loop stays converged)
+
+      if (q == 0) {
+        if (!SLOTG) xf_apply_pending(t, h);  // lazy tables: fold the pending batch step in first
+        if (part & 1) {
+          // the accumulated sum is rounded to float once (push_gradient is a float vector), then / rows
+          const float g = SLOTG ? xf_div_rows((float)h.g, rows) : gw[i];
+          xf_opt_coord(t, g, h.w, h.n, h.z);
         }
-        if (SLOTG) {
-          xf_ldv<VEC>(gvp + k, g);
+        if (SLOTG) h.g = -0.0;  // "untouched" marker for the next batch
+        if (K > 0 && (part & 2)) h.flags |= XF_FLAG_V_READY;
+        xf_store_head(rowp, h);  // one full-sector store
+      }
+      if (lat) {
+        const bool ready = (flags & XF_FLAG_V_READY) != 0;
+        for (int c = q; c < nchunk; c += tps) {
+          const int k = c * VEC;
+          float v[VEC], g[VEC], nn[VEC], zz[VEC];
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) g[e] = xf_div_rows(g[e], rows);
-        } else {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) g[e] = gv[i * (uint64_t)K + k + e];
-        }
-        if (t.opt == XF_OPT_FTRL) {
-          if (ready) { xf_ldv<VEC>(nvp + k, nn); xf_ldv<VEC>(zvp + k, zz); }
-          else {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) { nn[e] = 0.f; zz[e] = 0.f; }
+          for (int e = 0; e < VEC; ++e) { v[e] = v0[e]; nn[e] = n0[e]; zz[e] = z0[e]; }
+          if (c != q && ready) {  // K / VEC > 32 only
+            xf_ldv<VEC>(vp + k, v);
+            if (t.opt == XF_OPT_FTRL) { xf_ldv<VEC>(nvp + k, nn); xf_ldv<VEC>(zvp + k, zz); }
           }
+          if (!ready) {
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) xf_ftrl_coord(t, g[e], v[e], nn[e], zz[e]);
-          xf_stv<VEC>(nvp + k, nn);
-          xf_stv<VEC>(zvp + k, zz);
-        } else {
+            for (int e = 0; e < VEC; ++e) { v[e] = xf_v_init(t, key, (uint32_t)(k + e)); nn[e] = 0.f; zz[e] = 0.f; }
+          }
+          if (SLOTG) {
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) xf_sgd_coord(t, g[e], v[e]);
+            for (int e = 0; e < VEC; ++e) g[e] = xf_div_rows((float)(accA - (double)v[e] * accL), rows);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) g[e] = gv[i * (uint64_t)K + k + e];
+          }
+          if (t.opt == XF_OPT_FTRL) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) xf_ftrl_coord(t, g[e], v[e], nn[e], zz[e]);
+            xf_stv<VEC>(nvp + k, nn);
+            xf_stv<VEC>(zvp + k, zz);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) xf_sgd_coord(t, g[e], v[e]);
+          }
+          xf_stv<VEC>(vp + k, v);
         }
-        xf_stv<VEC>(vp + k, v);
         if (SLOTG) {
-          float zero[VEC];
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) zero[e] = 0.f;
-          xf_stv<VEC>(gvp + k, zero);
+          // every lane that needs the accumulators has consumed them by now
+          __syncwarp(group_mask);
+          if (q == 0) *reinterpret_cast<double2*>(xf_row_acc(rowp, K)) = make_double2(0.0, 0.0);
         }
       }
     }
@@ -233,7 +255,7 @@ __global__ void xf_k_import(XfTableView t, const uint32_t* __restrict__ slots, u
     } else if (v) {
       const int k = c - 1;
       xf_row_v(rowp)[k] = v[i * K + k];
-      xf_row_gv(rowp, K)[k] = 0.f;
+      if (k == 0) *reinterpret_cast<double2*>(xf_row_acc(rowp, K)) = make_double2(0.0, 0.0);
       if (t.opt == XF_OPT_FTRL) {
         xf_row_nv(rowp, K)[k] = nv ? nv[i * K + k] : 0.f;
         xf_row_zv(rowp, K)[k] = zv ? zv[i * K + k] : 0.f;
@@ -275,8 +297,8 @@ __global__ void xf_k_export(XfTableView t, const uint32_t* __restrict__ slots, c
         if (flags & XF_FLAG_V_READY) {
           vv = __ldcg(reinterpret_cast<const float*>(rowp + 32) + k);
           if (t.opt == XF_OPT_FTRL) {
-            nn = __ldcg(reinterpret_cast<const float*>(rowp + 32) + 2 * K + k);
-            zz = __ldcg(reinterpret_cast<const float*>(rowp + 32) + 3 * K + k);
+            nn = __ldcg(xf_row_nv(const_cast<uint8_t*>(rowp), K) + k);
+            zz = __ldcg(xf_row_zv(const_cast<uint8_t*>(rowp), K) + k);
           }
         } else {
           vv = xf_v_init(t, keys[i], (uint32_t)k);

@@ -18,6 +18,7 @@
 // float work on random sectors: no shared-memory tile, no tensor core — see DESIGN.md.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "table.cuh"
@@ -71,59 +72,16 @@ __device__ __forceinline__ void xf_fm_token(const XfTableView& t, uint32_t slot,
   }
 }
 
-// FM: add loss * (S - v_k) to the token's latent-gradient accumulators  (fm_worker.cc:141-142)
-template <int VEC>
-__device__ __forceinline__ void xf_fm_token_grad(const XfTableView& t, uint32_t slot, uint64_t key, float loss, float S) {
-  const int K = t.K;
-  uint8_t* rowp = xf_row(t, slot);
-  const float* vp = xf_row_v(rowp);
-  float* gvp = xf_row_gv(rowp, K);
-  const uint32_t flags = __ldca(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
-  const bool ready = (flags & XF_FLAG_V_READY) != 0;
-  for (int k = 0; k < K; k += VEC) {
-    float v[VEC], gc[VEC];
-    if (ready) {
-      xf_ldv_step<VEC>(vp + k, v);
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) v[e] = xf_v_init(t, key, (uint32_t)(k + e));
-    }
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) gc[e] = __fmul_rn(loss, __fsub_rn(S, v[e]));
-    xf_redv_step<VEC>(gvp + k, gc);
-  }
-}
-
-// Same terms, accumulated into a CTA-local shared-memory row instead of HBM (hot-key cache, see below)
-template <int VEC>
-__device__ __forceinline__ void xf_fm_token_grad_smem(const XfTableView& t, uint32_t slot, uint64_t key, float loss,
-                                                      float S, float* sgv) {
-  const int K = t.K;
-  const uint8_t* rowp = xf_row(t, slot);
-  const float* vp = reinterpret_cast<const float*>(rowp + 32);
-  const uint32_t flags = __ldca(reinterpret_cast<const uint32_t*>(rowp + XF_OFF_FLAGS));
-  const bool ready = (flags & XF_FLAG_V_READY) != 0;
-  for (int k = 0; k < K; k += VEC) {
-    float v[VEC];
-    if (ready) {
-      xf_ldv_step<VEC>(vp + k, v);
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) v[e] = xf_v_init(t, key, (uint32_t)(k + e));
-    }
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) atomicAdd(sgv + k + e, __fmul_rn(loss, __fsub_rn(S, v[e])));
-  }
-}
-
 // Hot-key cache (FM only): with skewed ids a handful of keys take a large share of all tokens (Zipf
 // 1.05 over 1e8 ids: the top key is ~8 % of the tokens of every batch) and their L2 atomics serialise
 // the whole kernel (measured: 3.7 ms per cfg5-shaped batch, 17 contended atomics per token).  Each CTA
 // therefore keeps NC direct-mapped accumulator rows in shared memory, claimed first-come with a CAS on
 // the tag; a token whose key owns (or obtains) an entry accumulates there with shared-memory atomics,
 // everything else goes to HBM as before.  The entries are flushed once, when the CTA has finished all
-// its rows: NC x (1 + K/4) global atomics per CTA instead of one set per token.  Sums are unchanged
-// (same terms, different association).  touched[] gets gridDim.x * NC extra positions for the flush.
+// its rows: 3 global atomics per entry and CTA instead of one set per token.  Sums are unchanged (same
+// terms, different association).  touched[] gets gridDim.x * NC extra positions for the flush.
+// Per (group of) token(s) the step adds three doubles to the key: G (the w-gradient), L = loss and
+// Aq = loss * S (the factorised latent gradient, table.cuh); loss * S is exact in double.
 //   mode: 0 = train, 1 = predict (forward only; the Pull still inserts missing keys, lr_worker.cc:47)
 template <bool FM, int VEC>
 __global__ void __launch_bounds__(256)
@@ -139,14 +97,13 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
   const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * warps_per_block;
   const int K = t.K;
-  // hot-key cache layout: double gw[NC] | float gv[NC*K] | uint32 tag[NC]
+  // hot-key cache layout: double acc[NC][3] = {G, L, Aq} | uint32 tag[NC]
   const int NC = (FM && log2nc >= 0) ? (1 << log2nc) : 0;
-  double* c_gw = reinterpret_cast<double*>(xf_smem);
-  float* c_gv = reinterpret_cast<float*>(xf_smem + (size_t)NC * 8);
-  uint32_t* c_tag = reinterpret_cast<uint32_t*>(xf_smem + (size_t)NC * 8 + (size_t)NC * K * 4);
+  double* c_acc = reinterpret_cast<double*>(xf_smem);
+  uint32_t* c_tag = reinterpret_cast<uint32_t*>(xf_smem + (size_t)NC * 24);
   if (NC) {
-    for (int e = threadIdx.x; e < NC; e += blockDim.x) { c_tag[e] = XF_NO_SLOT; c_gw[e] = 0.0; }
-    for (int e = threadIdx.x; e < NC * K; e += blockDim.x) c_gv[e] = 0.f;
+    for (int e = threadIdx.x; e < NC; e += blockDim.x) c_tag[e] = XF_NO_SLOT;
+    for (int e = threadIdx.x; e < NC * 3; e += blockDim.x) c_acc[e] = 0.0;
     __syncthreads();
   }
 
@@ -237,7 +194,8 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
       const unsigned g1 = __match_any_sync(0xffffffffu, (s1 != XF_NO_SLOT) ? s1 : (0xFFFFFF00u | (uint32_t)lane));
       const bool lead0 = s0 != XF_NO_SLOT && lane == __ffs(g0) - 1;
       const bool lead1 = s1 != XF_NO_SLOT && lane == __ffs(g1) - 1;
-      const float c0 = (float)__popc(g0), c1 = (float)__popc(g1);
+      const double c0 = (double)__popc(g0), c1 = (double)__popc(g1);
+      const double ld = (double)loss, ad = (double)loss * (double)S;  // exact products
       double old0 = 0.0, old1 = 0.0;
       bool cached0 = false, cached1 = false;
       if (NC) {
@@ -247,8 +205,9 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
           const uint32_t prev = atomicCAS(c_tag + e, XF_NO_SLOT, s0);
           if (prev == XF_NO_SLOT || prev == s0) {
             cached0 = true;
-            atomicAdd(c_gw + e, gw_d * (double)c0);
-            xf_fm_token_grad_smem<VEC>(t, s0, __ldg(keys + j0), __fmul_rn(loss, c0), S, c_gv + (size_t)e * K);
+            atomicAdd(c_acc + 3 * e, gw_d * c0);
+            atomicAdd(c_acc + 3 * e + 1, ld * c0);
+            atomicAdd(c_acc + 3 * e + 2, ad * c0);
           }
         }
         if (lead1) {
@@ -256,16 +215,17 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
           const uint32_t prev = atomicCAS(c_tag + e, XF_NO_SLOT, s1);
           if (prev == XF_NO_SLOT || prev == s1) {
             cached1 = true;
-            atomicAdd(c_gw + e, gw_d * (double)c1);
-            xf_fm_token_grad_smem<VEC>(t, s1, __ldg(keys + j1), __fmul_rn(loss, c1), S, c_gv + (size_t)e * K);
+            atomicAdd(c_acc + 3 * e, gw_d * c1);
+            atomicAdd(c_acc + 3 * e + 1, ld * c1);
+            atomicAdd(c_acc + 3 * e + 2, ad * c1);
           }
         }
       }
-      if (lead0 && !cached0) old0 = atomicAdd(xf_row_g(xf_row(t, s0)), gw_d * (double)c0);
-      if (lead1 && !cached1) old1 = atomicAdd(xf_row_g(xf_row(t, s1)), gw_d * (double)c1);
+      if (lead0 && !cached0) old0 = atomicAdd(xf_row_g(xf_row(t, s0)), gw_d * c0);
+      if (lead1 && !cached1) old1 = atomicAdd(xf_row_g(xf_row(t, s1)), gw_d * c1);
       if (FM) {
-        if (lead0 && !cached0) xf_fm_token_grad<VEC>(t, s0, __ldg(keys + j0), __fmul_rn(loss, c0), S);
-        if (lead1 && !cached1) xf_fm_token_grad<VEC>(t, s1, __ldg(keys + j1), __fmul_rn(loss, c1), S);
+        if (lead0 && !cached0) { double* a = xf_row_acc(xf_row(t, s0), K); atomicAdd(a, ld * c0); atomicAdd(a + 1, ad * c0); }
+        if (lead1 && !cached1) { double* a = xf_row_acc(xf_row(t, s1), K); atomicAdd(a, ld * c1); atomicAdd(a + 1, ad * c1); }
       }
       const bool f0 = lead0 && !cached0 && (unsigned long long)__double_as_longlong(old0) == XF_NEG_ZERO_BITS64;
       const bool f1 = lead1 && !cached1 && (unsigned long long)__double_as_longlong(old1) == XF_NEG_ZERO_BITS64;
@@ -282,15 +242,11 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
       uint32_t rec = XF_NO_SLOT;
       if (s != XF_NO_SLOT) {
         uint8_t* rowp = xf_row(t, s);
-        const double old = atomicAdd(xf_row_g(rowp), c_gw[e]);
+        const double old = atomicAdd(xf_row_g(rowp), c_acc[3 * e]);
         if ((unsigned long long)__double_as_longlong(old) == XF_NEG_ZERO_BITS64) rec = s;
-        float* gvp = xf_row_gv(rowp, K);
-        for (int k = 0; k < K; k += VEC) {
-          float gc[VEC];
-#pragma unroll
-          for (int x = 0; x < VEC; ++x) gc[x] = c_gv[(size_t)e * K + k + x];
-          xf_redv_step<VEC>(gvp + k, gc);
-        }
+        double* a = xf_row_acc(rowp, K);
+        atomicAdd(a, c_acc[3 * e + 1]);
+        atomicAdd(a + 1, c_acc[3 * e + 2]);
       }
       touched[touched_base + (uint32_t)blockIdx.x * (uint32_t)NC + (uint32_t)e] = rec;
     }
@@ -435,11 +391,15 @@ xf_k_step_ws(XfWorkSet ws, const uint32_t* __restrict__ row_ptr, const uint64_t*
 int xf_sms();
 int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm);
 
-// shared-memory hot-key cache sizing for the FM step: NC entries of (8 + 4K + 4) bytes, <= 24 KB per CTA
+// shared-memory hot-key cache sizing for the FM step: NC entries of 3 doubles + a tag (28 bytes)
+#define XF_STEP_CACHE_LOG2 9
 int xf_step_cache_log2(int K) {
   if (K <= 0) return -1;
-  int lg = 8;
-  while (lg > 0 && ((size_t)1 << lg) * (12 + 4 * (size_t)K) > 24 * 1024) --lg;
+  static const int lg = [] {
+    const char* e = getenv("XFLOW_FM_CACHE_LOG2");  // tuning knob; 0..10
+    const int v = (e && *e) ? atoi(e) : XF_STEP_CACHE_LOG2;
+    return v < 0 ? 0 : (v > 10 ? 10 : v);
+  }();
   return lg;
 }
 // extra touched[] positions the FM step needs beyond nnz (grid x NC)
@@ -456,7 +416,7 @@ void xf_launch_step(const XfTableView& t, const uint32_t* row_ptr, const uint64_
   const int block = 256;
   const int grid = xf_grid_for((uint64_t)B * 32, block, 8);
   const int lg = xf_step_cache_log2(t.K);
-  const size_t smem = lg >= 0 ? ((size_t)1 << lg) * (12 + 4 * (size_t)t.K) : 0;
+  const size_t smem = lg >= 0 ? ((size_t)1 << lg) * 28 : 0;
 #define XF_STEP_ARGS t, row_ptr, keys, labels, B, mode, touched, loss_out, pctr_out, abs_loss_sum, lg, nnz
   if (t.K == 0) {
     xf_k_step<false, 1><<<grid, block, 0, st>>>(XF_STEP_ARGS);

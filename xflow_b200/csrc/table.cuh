@@ -17,10 +17,15 @@
 //                                more accurate than the reference's own sequential float sum).
 //   ---- 32 B = one DRAM sector: an LR pull, gradient accumulate or update touches exactly one ----
 //   byte 32            f32 v[K]    app-1 latent row
-//   byte 32 +   4K     f32 gv[K]   per-batch gradient accumulator of v
-//   byte 32 +   8K     f32 nv[K]   (FTRL only)
-//   byte 32 +  12K     f32 zv[K]   (FTRL only)
-//   row stride = round_up(32 + nblk*4K, 32), nblk = 4 (FTRL) / 2 (SGD).
+//   byte A             f64 L, f64 Aq   per-batch latent-gradient accumulators, A = round_up(32 + 4K, 16).
+//                                  The reference's gv[i,k] = sum_occ loss_s * (S_s - v[i,k])
+//                                  (fm_worker.cc:141-142) factorises as Aq_i - v[i,k] * L_i with
+//                                  L_i = sum_occ loss_s and Aq_i = sum_occ loss_s * S_s: two f64
+//                                  accumulators per key instead of K float ones (3 atomics per token
+//                                  instead of 1 + K/4 vector ones, and no second read of v).
+//   byte A + 16        f32 nv[K]   (FTRL only)
+//   byte A + 16 + 4K   f32 zv[K]   (FTRL only)
+//   row stride = round_up(A + 16 + (FTRL ? 8K : 0), 32): K = 16 FTRL -> 256 B.
 //
 // Missing keys are inserted on first touch by a pull OR a push, like `store[key]`
 // (ftrl.h:56,114-120 ; sgd.h:48,92).  Default contents: w = n = z = 0 ; v per init mode.  The latent
@@ -62,9 +67,10 @@ struct XfTableView {
 };
 #define XF_TAG_LOCKED 0xFFFFFFFFu
 
+__host__ __device__ inline uint32_t xf_acc_off(int K) { return (32u + 4u * (uint32_t)K + 15u) & ~15u; }
 __host__ __device__ inline uint32_t xf_row_stride(int K, int opt) {
-  uint32_t nblk = (opt == XF_OPT_FTRL) ? 4u : 2u;
-  uint32_t bytes = 32u + nblk * 4u * (uint32_t)K;
+  if (K <= 0) return 32u;
+  uint32_t bytes = xf_acc_off(K) + 16u + ((opt == XF_OPT_FTRL) ? 8u * (uint32_t)K : 0u);
   return (bytes + 31u) & ~31u;
 }
 
@@ -107,9 +113,9 @@ __device__ __forceinline__ uint8_t* xf_row(const XfTableView& t, uint64_t slot) 
 __device__ __forceinline__ double* xf_row_g(uint8_t* row) { return reinterpret_cast<double*>(row + 24); }
 #define XF_OFF_FLAGS 20
 __device__ __forceinline__ float* xf_row_v(uint8_t* row) { return reinterpret_cast<float*>(row + 32); }
-__device__ __forceinline__ float* xf_row_gv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + 32) + K; }
-__device__ __forceinline__ float* xf_row_nv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + 32) + 2 * K; }
-__device__ __forceinline__ float* xf_row_zv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + 32) + 3 * K; }
+__device__ __forceinline__ double* xf_row_acc(uint8_t* row, int K) { return reinterpret_cast<double*>(row + xf_acc_off(K)); }
+__device__ __forceinline__ float* xf_row_nv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + xf_acc_off(K) + 16); }
+__device__ __forceinline__ float* xf_row_zv(uint8_t* row, int K) { return xf_row_nv(row, K) + K; }
 
 struct XfHead {
   uint64_t key;
