@@ -55,7 +55,7 @@ __device__ __forceinline__ void xf_wait_open(const XfTableView& t, const uint8_t
 // fold the pending step (batch h.flags, `rows` rows) into the snapshot and stamp it open for `seq`
 __device__ __forceinline__ void xf_open_snapshot(const XfTableView& t, XfHead& h, uint32_t rows, uint32_t seq) {
   if (h.flags != 0u) {
-    const float g = xf_div_rows((float)h.g, (double)rows);  // lr_worker.cc:116-118
+    const float g = xf_div_rows_plain((float)h.g, (double)rows);  // lr_worker.cc:116-118 (the fast path spills here)
     xf_opt_coord(t, g, h.w, h.n, h.z);                       // ftrl.h:59-74 / sgd.h:52
   }
   h.flags = seq;

@@ -251,7 +251,18 @@ __device__ __forceinline__ void xf_opt_coord(const XfTableView& t, float g, floa
 }
 
 // push_gradient[i] /= 1.0 * loss.size()  lr_worker.cc:116-118 ; fm_worker.cc:150-156 (double divide)
-__device__ __forceinline__ float xf_div_rows(float g, double rows) { return (float)((double)g / rows); }
+__device__ __forceinline__ float xf_div_rows_plain(float g, double rows) { return (float)((double)g / rows); }
+__device__ __forceinline__ float xf_div_rows(float g, double rows) {
+  // A power-of-two row count (the usual batch size) makes the quotient an exact scaling: multiplying by
+  // the exact reciprocal gives the same double, hence the same float, without a double division (the
+  // update kernel was instruction-bound on it, profiles/r01_ncu_full_fm_ftrl.md).
+  const long long b = __double_as_longlong(rows);
+  if ((b & 0x000FFFFFFFFFFFFFll) == 0ll && b > 0ll) {
+    const double inv = __longlong_as_double((2046ll << 52) - b);  // 2^-e for rows = 2^e
+    return (float)((double)g * inv);
+  }
+  return (float)((double)g / rows);
+}
 
 // Lazy tables: the row as the reference's server would hold it — i.e. with the pending optimizer step
 // (the Push of the batch named by the tag) applied.  Pure function of the snapshot; writes nothing.
@@ -262,7 +273,7 @@ __device__ __forceinline__ void xf_apply_pending(const XfTableView& t, XfHead& h
   if (!xf_has_pending(t, h)) return;
   const double rows = (double)__ldg(t.rows_by_seq + h.flags);
   // the residual sum is rounded to float once (push_gradient is a float vector), then divided
-  const float g = xf_div_rows((float)h.g, rows);
+  const float g = xf_div_rows_plain((float)h.g, rows);
   xf_opt_coord(t, g, h.w, h.n, h.z);
   h.flags = 0u;
   h.g = 0.0;
