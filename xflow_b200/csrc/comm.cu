@@ -227,8 +227,11 @@ __global__ void xf_k_ws_grads(XfWorkSet ws, XfBucketCounts cnt, double rows, int
     } else {
       const uint64_t y = x - n;  // in [0, n*K)
       const uint64_t idx = (uint64_t)q * ws.cap * K + y;
-      if (want_grads) grad_v[idx] = xf_div_rows(ws.gv[idx], rows);     // fm_worker.cc:154-156
-      ws.gv[idx] = 0.f;
+      // latent gradient from the factorised sums: gv[u,k] = Aq[u] - v[u,k] * L[u]  (fm_worker.cc:141-142,154-156);
+      // the accumulators are cleared by the caller once every coordinate has read them
+      const uint64_t ul = y / (uint64_t)K;
+      const double2 a = __ldcg(reinterpret_cast<const double2*>(ws.acc) + ((uint64_t)q * ws.cap + ul));
+      if (want_grads) grad_v[idx] = xf_div_rows((float)(a.y - (double)ws.v[idx] * a.x), rows);
     }
   }
 }
@@ -243,7 +246,7 @@ struct XfMg {
   // allgather) while batch b's gradients travel and its owner updates run on the table stream.
   XfWorkSet ws2[2];
   size_t set_bytes = 0;
-  XfDevBuf d_set[2], d_keys[2], d_w[2], d_v[2], d_gw[2], d_gv[2], grad_w[2], grad_v[2], bucket_cnt[2], all_counts;
+  XfDevBuf d_set[2], d_keys[2], d_w[2], d_v[2], d_gw[2], d_acc[2], grad_w[2], grad_v[2], bucket_cnt[2], all_counts;
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_free[2] = {nullptr, nullptr};  // work set no longer read by the table stream
   uint64_t step_no = 0;
@@ -291,12 +294,12 @@ int xf_mg_create(xf_trainer* tr) {
     XF_TRY(mg->grad_w[b].ensure(tot * 4));
     if (K) {
       XF_TRY(mg->d_v[b].ensure(tot * 4 * K));
-      XF_TRY(mg->d_gv[b].ensure(tot * 4 * K));
+      XF_TRY(mg->d_acc[b].ensure(tot * 16));
       XF_TRY(mg->grad_v[b].ensure(tot * 4 * K));
     }
     XF_TRY(mg->bucket_cnt[b].ensure((size_t)S * 4));
     XF_CUDA_TRY(cudaMemsetAsync(mg->d_gw[b].p, 0, tot * 8, st));
-    if (K) XF_CUDA_TRY(cudaMemsetAsync(mg->d_gv[b].p, 0, tot * 4 * K, st));
+    if (K) XF_CUDA_TRY(cudaMemsetAsync(mg->d_acc[b].p, 0, tot * 16, st));
     XF_CUDA_TRY(cudaEventCreateWithFlags(&mg->ev_free[b], cudaEventDisableTiming));
     XfWorkSet& w = mg->ws2[b];
     w.set = mg->d_set[b].as<uint8_t>();
@@ -308,7 +311,7 @@ int xf_mg_create(xf_trainer* tr) {
     w.w = mg->d_w[b].as<float>();
     w.v = K ? mg->d_v[b].as<float>() : nullptr;
     w.gw = mg->d_gw[b].as<double>();
-    w.gv = K ? mg->d_gv[b].as<float>() : nullptr;
+    w.acc = K ? mg->d_acc[b].as<double>() : nullptr;
   }
   XF_TRY(mg->all_counts.ensure((size_t)S * S * 4));
   XF_CUDA_TRY(cudaStreamSynchronize(st));
@@ -349,7 +352,7 @@ void xf_mg_destroy(xf_trainer* tr) {
   }
   cudaStreamSynchronize(mg->st2);
   for (int b = 0; b < 2; ++b) {
-    XfDevBuf* pb[] = {&mg->d_set[b], &mg->d_keys[b], &mg->d_w[b], &mg->d_v[b], &mg->d_gw[b], &mg->d_gv[b],
+    XfDevBuf* pb[] = {&mg->d_set[b], &mg->d_keys[b], &mg->d_w[b], &mg->d_v[b], &mg->d_gw[b], &mg->d_acc[b],
                       &mg->grad_w[b], &mg->grad_v[b], &mg->bucket_cnt[b]};
     for (XfDevBuf* x : pb) x->release();
     if (mg->ev_free[b]) cudaEventDestroy(mg->ev_free[b]);
@@ -483,6 +486,8 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
     xf_k_ws_grads<<<grid, 256, 0, st>>>(ws, bc, (double)rows, 1, mg->grad_w[cur].as<float>(),
                                         K ? mg->grad_v[cur].as<float>() : nullptr);
     ++tr->launches;
+    // {L, Aq} of the used part of every bucket back to zero (one strided memset)
+    if (K) XF_CUDA_TRY(cudaMemset2DAsync(ws.acc, (size_t)ws.cap * 16, 0, (size_t)max_bucket * 16, (size_t)S, st));
   }
 
   // ---- all-to-all #3: gradients to the owners (the Push, kv_app.h:110-118)

@@ -271,14 +271,24 @@ template <bool FM, int VEC>
 __global__ void __launch_bounds__(256)
 xf_k_step_ws(XfWorkSet ws, const uint32_t* __restrict__ row_ptr, const uint64_t* __restrict__ keys,
              const uint8_t* __restrict__ labels, int B, int mode, float* __restrict__ loss_out,
-             float* __restrict__ pctr_out, float* __restrict__ abs_loss_sum) {
+             float* __restrict__ pctr_out, float* __restrict__ abs_loss_sum, int log2nc) {
   __shared__ float s_abs[8];
+  extern __shared__ __align__(16) unsigned char xf_smem[];
   float abs_acc = 0.f;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * warps_per_block;
   const int K = ws.K;
+  // CTA hot-key cache, as in xf_k_step: double acc[NC][3] = {G, L, Aq} | uint32 tag[NC] (tag = u)
+  const int NC = (FM && log2nc >= 0 && mode == 0) ? (1 << log2nc) : 0;
+  double* c_acc = reinterpret_cast<double*>(xf_smem);
+  uint32_t* c_tag = reinterpret_cast<uint32_t*>(xf_smem + (size_t)NC * 24);
+  if (NC) {
+    for (int e = threadIdx.x; e < NC; e += blockDim.x) c_tag[e] = XF_NO_SLOT;
+    for (int e = threadIdx.x; e < NC * 3; e += blockDim.x) c_acc[e] = 0.0;
+    __syncthreads();
+  }
 
   for (int row = gwarp; row < B; row += nwarps) {
     const uint32_t beg = __ldg(row_ptr + row);
@@ -296,8 +306,8 @@ xf_k_step_ws(XfWorkSet ws, const uint32_t* __restrict__ row_ptr, const uint64_t*
       const uint64_t k1 = j1 < end ? __ldcs(keys + j1) : 0ull;
       const uint32_t u0 = j0 < end ? xf_ws_find(ws, k0) : XF_NO_SLOT;
       const uint32_t u1 = j1 < end ? xf_ws_find(ws, k1) : XF_NO_SLOT;
-      if (u0 != XF_NO_SLOT) wsum += __ldcg(ws.w + u0);
-      if (u1 != XF_NO_SLOT) wsum += __ldcg(ws.w + u1);
+      if (u0 != XF_NO_SLOT) wsum += __ldca(ws.w + u0);  // read-only here: L1 keeps the hot keys SM-local
+      if (u1 != XF_NO_SLOT) wsum += __ldca(ws.w + u1);
       if (FM) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -360,21 +370,34 @@ xf_k_step_ws(XfWorkSet ws, const uint32_t* __restrict__ row_ptr, const uint64_t*
         // same-key tokens of the row are merged: the group's lowest lane adds count x term
         const unsigned grp = __match_any_sync(0xffffffffu, (u != XF_NO_SLOT) ? u : (0xFFFFFF00u | (uint32_t)lane));
         if (u == XF_NO_SLOT || lane != __ffs(grp) - 1) continue;
-        const float cnt = (float)__popc(grp);
-        atomicAdd(ws.gw + u, gw_d * (double)cnt);
-        if (FM) {
-          const float lc = __fmul_rn(loss, cnt);
-          const float* vp = ws.v + (uint64_t)u * K;
-          float* gvp = ws.gv + (uint64_t)u * K;
-          for (int k = 0; k < K; k += VEC) {
-            float v[VEC], gc[VEC];
-            xf_ldv_step<VEC>(vp + k, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) gc[e] = __fmul_rn(lc, __fsub_rn(S, v[e]));
-            xf_redv_step<VEC>(gvp + k, gc);
+        const double cnt = (double)__popc(grp);
+        const double gd = gw_d * cnt, ld = (double)loss * cnt, ad = (double)loss * (double)S * cnt;  // exact products
+        bool cached = false;
+        if (NC) {
+          const uint32_t e = (u * 2654435761u) >> (32 - log2nc);
+          const uint32_t prev = atomicCAS(c_tag + e, XF_NO_SLOT, u);
+          if (prev == XF_NO_SLOT || prev == u) {
+            cached = true;
+            atomicAdd(c_acc + 3 * e, gd);
+            atomicAdd(c_acc + 3 * e + 1, ld);
+            atomicAdd(c_acc + 3 * e + 2, ad);
           }
         }
+        if (!cached) {
+          atomicAdd(ws.gw + u, gd);
+          if (FM) { atomicAdd(ws.acc + 2 * (uint64_t)u, ld); atomicAdd(ws.acc + 2 * (uint64_t)u + 1, ad); }
+        }
       }
+    }
+  }
+  if (NC) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < NC; e += blockDim.x) {
+      const uint32_t u = c_tag[e];
+      if (u == XF_NO_SLOT) continue;
+      atomicAdd(ws.gw + u, c_acc[3 * e]);
+      atomicAdd(ws.acc + 2 * (uint64_t)u, c_acc[3 * e + 1]);
+      atomicAdd(ws.acc + 2 * (uint64_t)u + 1, c_acc[3 * e + 2]);
     }
   }
   if (abs_loss_sum != nullptr && mode == 0) {
@@ -435,14 +458,16 @@ void xf_launch_step_ws(const XfWorkSet& ws, const uint32_t* row_ptr, const uint6
   if (B <= 0) return;
   const int block = 256;
   const int grid = xf_grid_for((uint64_t)B * 32, block, 8);
-#define XF_WS_ARGS ws, row_ptr, keys, labels, B, mode, loss_out, pctr_out, abs_loss_sum
+  const int lg = xf_step_cache_log2(ws.K);
+  const size_t smem = lg >= 0 ? ((size_t)1 << lg) * 28 : 0;
+#define XF_WS_ARGS ws, row_ptr, keys, labels, B, mode, loss_out, pctr_out, abs_loss_sum, lg
   if (ws.K == 0) {
     xf_k_step_ws<false, 1><<<grid, block, 0, st>>>(XF_WS_ARGS);
   } else {
     switch (xf_vec_for(ws.K)) {
-      case 4: xf_k_step_ws<true, 4><<<grid, block, 0, st>>>(XF_WS_ARGS); break;
-      case 2: xf_k_step_ws<true, 2><<<grid, block, 0, st>>>(XF_WS_ARGS); break;
-      default: xf_k_step_ws<true, 1><<<grid, block, 0, st>>>(XF_WS_ARGS); break;
+      case 4: xf_k_step_ws<true, 4><<<grid, block, smem, st>>>(XF_WS_ARGS); break;
+      case 2: xf_k_step_ws<true, 2><<<grid, block, smem, st>>>(XF_WS_ARGS); break;
+      default: xf_k_step_ws<true, 1><<<grid, block, smem, st>>>(XF_WS_ARGS); break;
     }
   }
 #undef XF_WS_ARGS

@@ -9,7 +9,8 @@
 //   u       = owner_shard * cap + position inside that owner's bucket  (bucket-major, so bucket q of
 //           every array is one contiguous NCCL send / receive)
 //   keys[u] the unique keys (Pull request)      w[u], v[u*K+k]  pulled values (Pull response)
-//   gw[u] (f64), gv[u*K+k] (f32) gradient accumulators -> grad_w / grad_v (Push payload)
+//   gw[u] (f64), acc[2u] = {L, Aq} (f64) gradient accumulators -> grad_w / grad_v (Push payload); the
+//           latent gradient is factorised like in the table (table.cuh): gv[u,k] = Aq[u] - v[u,k] * L[u]
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,7 +25,7 @@ struct XfWorkSet {
   float* w;
   float* v;
   double* gw;
-  float* gv;
+  double* acc;  // {L, Aq} per key (FM only)
 };
 
 struct XfBucketCounts {
@@ -39,7 +40,8 @@ __device__ __forceinline__ uint64_t xf_ws_hash(uint64_t key, uint32_t log2cap) {
 __device__ __forceinline__ uint32_t xf_ws_find(const XfWorkSet& ws, uint64_t key) {
   uint64_t s = xf_ws_hash(key, ws.log2cap);
   for (int probes = 0; probes < 8192; ++probes) {
-    const uint4 e = __ldcg(reinterpret_cast<const uint4*>(ws.set + s * 16));
+    // through L1: the set is read-only once the dedup kernel has finished, and hot keys stay SM-local
+    const uint4 e = __ldca(reinterpret_cast<const uint4*>(ws.set + s * 16));
     const uint64_t k = (uint64_t)e.x | ((uint64_t)e.y << 32);
     if (k == key) return e.z;
     if (k == 0xFFFFFFFFFFFFFFFFull) return 0xFFFFFFFFu;
