@@ -251,8 +251,16 @@ struct XfMg {
   cudaEvent_t ev_free[2] = {nullptr, nullptr};  // work set no longer read by the table stream
   uint64_t step_no = 0;
   XfDevBuf recv_keys, recv_slots, resp_w, resp_v, rgrad_w, rgrad_v;   // owner side, grouped by source
+  // Peer-memory exchange (default when cudaIpc works; XFLOW_P2P=0 keeps the NCCL send/recv groups):
+  // every buffer a peer reads is exported once with cudaIpcGetMemHandle and mapped by all ranks; an
+  // exchange is then a handful of DMA reads from peer memory (cudaMemcpyAsync) behind a tiny NCCL
+  // all-reduce that orders "producer finished" across ranks on the table stream.
+  bool p2p = false;
+  enum { PEER_KEYS0 = 0, PEER_KEYS1, PEER_GW0, PEER_GW1, PEER_GV0, PEER_GV1, PEER_RESP_W, PEER_RESP_V, PEER_NBUF };
+  void* peer[XF_MG_MAX_SHARDS][PEER_NBUF];
+  int* d_barrier = nullptr;
   uint32_t* h_counts = nullptr;        // pinned S*S
-  std::vector<uint64_t> send_off, recv_off, send_cnt, recv_cnt;
+  std::vector<uint64_t> send_off, recv_off, send_cnt, recv_cnt, own_off, resp_off;
   // XFLOW_MG_TRACE=1: CUDA events at the phase boundaries of every step, averages printed at destroy
   bool trace = false;
   std::vector<cudaEvent_t> tev;
@@ -263,6 +271,103 @@ static const char* kMgPhase[] = {"set clear + dedup", "counts allgather+sync", "
                                  "(unused)", "fused step (work set)", "grads", "a2a grads", "owner updates"};
 #define XF_MG_TRACE_STEPS 512
 #define XF_MG_MARK(i) do { if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) cudaEventRecord(mg->tev[mg->tsteps * 11 + (i)], st); } while (0)
+
+// ---- peer-memory exchange ------------------------------------------------------------------------
+static int xf_mg_barrier(xf_comm* c, XfMg* mg, cudaStream_t st) {
+  XF_NCCL_TRY(g_nccl.AllReduce(mg->d_barrier, mg->d_barrier, 1, ncclInt, ncclSum, c->nccl, st));
+  return XF_OK;
+}
+
+static void* xf_mg_local_buf(XfMg* mg, int i) {
+  switch (i) {
+    case XfMg::PEER_KEYS0: return mg->d_keys[0].p;
+    case XfMg::PEER_KEYS1: return mg->d_keys[1].p;
+    case XfMg::PEER_GW0: return mg->grad_w[0].p;
+    case XfMg::PEER_GW1: return mg->grad_w[1].p;
+    case XfMg::PEER_GV0: return mg->grad_v[0].p;
+    case XfMg::PEER_GV1: return mg->grad_v[1].p;
+    case XfMg::PEER_RESP_W: return mg->resp_w.p;
+    case XfMg::PEER_RESP_V: return mg->resp_v.p;
+  }
+  return nullptr;
+}
+
+// Export this rank's exchange buffers, import everybody else's.  Any failure on any rank (no IPC in this
+// container, no peer access) leaves p2p off everywhere: the decision is agreed through an all-reduce.
+static int xf_mg_setup_p2p(xf_trainer* tr, XfMg* mg, size_t tot, size_t K) {
+  xf_comm* c = tr->comm;
+  const int S = mg->S;
+  memset(mg->peer, 0, sizeof(mg->peer));
+  const char* e = getenv("XFLOW_P2P");
+  const bool want = !(e && *e == '0');
+  cudaStream_t st = tr->table->stream;
+  XF_CUDA_TRY(cudaMalloc(&mg->d_barrier, sizeof(int)));
+  XF_CUDA_TRY(cudaMemsetAsync(mg->d_barrier, 0, sizeof(int), st));
+  // peers read the Pull responses in place: fixed size, never reallocated
+  XF_TRY(mg->resp_w.ensure(tot * 4 + 4));
+  if (K) XF_TRY(mg->resp_v.ensure(tot * 4 * K + 4));
+  struct Pack { cudaIpcMemHandle_t h[XfMg::PEER_NBUF]; int ok; int pad[15]; };
+  std::vector<Pack> all((size_t)S);
+  Pack mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.ok = want ? 1 : 0;
+  for (int i = 0; i < XfMg::PEER_NBUF && mine.ok; ++i) {
+    void* p = xf_mg_local_buf(mg, i);
+    if (p && cudaIpcGetMemHandle(&mine.h[i], p) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  }
+  XfDevBuf d_all;
+  XF_TRY(d_all.ensure(sizeof(Pack) * (size_t)S));
+  XF_CUDA_TRY(cudaMemcpyAsync((char*)d_all.p + sizeof(Pack) * (size_t)mg->rank, &mine, sizeof(Pack), cudaMemcpyHostToDevice, st));
+  XF_NCCL_TRY(g_nccl.AllGather((char*)d_all.p + sizeof(Pack) * (size_t)mg->rank, d_all.p, sizeof(Pack), ncclChar, c->nccl, st));
+  XF_CUDA_TRY(cudaMemcpyAsync(all.data(), d_all.p, sizeof(Pack) * (size_t)S, cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  int ok = 1;
+  for (int q = 0; q < S; ++q) ok &= all[q].ok;
+  if (ok) {
+    for (int q = 0; q < S && ok; ++q) {
+      if (q == mg->rank) continue;
+      for (int i = 0; i < XfMg::PEER_NBUF && ok; ++i) {
+        if (!xf_mg_local_buf(mg, i)) continue;  // same set of buffers on every rank
+        if (cudaIpcOpenMemHandle(&mg->peer[q][i], all[q].h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          mg->peer[q][i] = nullptr;
+          ok = 0;
+        }
+      }
+    }
+  }
+  // agree on the outcome
+  int flag = ok ? 0 : 1;
+  XF_CUDA_TRY(cudaMemcpyAsync(mg->d_barrier, &flag, sizeof(int), cudaMemcpyHostToDevice, st));
+  XF_TRY(xf_mg_barrier(c, mg, st));
+  XF_CUDA_TRY(cudaMemcpyAsync(&flag, mg->d_barrier, sizeof(int), cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  XF_CUDA_TRY(cudaMemsetAsync(mg->d_barrier, 0, sizeof(int), st));
+  d_all.release();
+  mg->p2p = (flag == 0);
+  if (!mg->p2p) {
+    for (int q = 0; q < S; ++q)
+      for (int i = 0; i < XfMg::PEER_NBUF; ++i)
+        if (mg->peer[q][i]) { cudaIpcCloseMemHandle(mg->peer[q][i]); mg->peer[q][i] = nullptr; }
+  }
+  if (getenv("XFLOW_MG_TRACE")) fprintf(stderr, "[xflow mg] rank %d: peer-memory exchange %s\n", mg->rank, mg->p2p ? "on" : "off (NCCL send/recv)");
+  return XF_OK;
+}
+
+// One exchange as peer reads: segment q of `dst` (element offset doff[q], cnt[q] keys) is copied from rank
+// q's exported buffer `which`, where it starts at element offset soff[q].  The caller has already ordered
+// "rank q finished writing" before this point of the stream (bucket-size allgather or xf_mg_barrier).
+static int xf_mg_pull(XfMg* mg, int which, const void* local_src, const std::vector<uint64_t>& soff, void* dst,
+                      const std::vector<uint64_t>& doff, const std::vector<uint64_t>& cnt, size_t bytes_per_key,
+                      cudaStream_t st) {
+  for (int q = 0; q < mg->S; ++q) {
+    if (!cnt[q]) continue;
+    const char* src = (q == mg->rank) ? (const char*)local_src : (const char*)mg->peer[q][which];
+    XF_CUDA_TRY(cudaMemcpyAsync((char*)dst + doff[q] * bytes_per_key, src + soff[q] * bytes_per_key, cnt[q] * bytes_per_key,
+                                cudaMemcpyDeviceToDevice, st));
+  }
+  return XF_OK;
+}
 
 int xf_mg_create(xf_trainer* tr) {
   xf_comm* c = tr->comm;
@@ -320,6 +425,8 @@ int xf_mg_create(xf_trainer* tr) {
   mg->recv_off.resize(S + 1);
   mg->send_cnt.resize(S);
   mg->recv_cnt.resize(S);
+  mg->own_off.resize(S);
+  mg->resp_off.resize(S);
   const char* tenv = getenv("XFLOW_MG_TRACE");
   mg->trace = tenv && *tenv == '1';
   if (mg->trace) {
@@ -327,6 +434,8 @@ int xf_mg_create(xf_trainer* tr) {
     for (auto& e : mg->tev) cudaEventCreate(&e);
   }
   tr->mg = mg;
+  int rc = xf_mg_setup_p2p(tr, mg, tot, K);
+  if (rc != XF_OK) { xf_mg_destroy(tr); return rc; }
   return XF_OK;
 }
 
@@ -351,6 +460,15 @@ void xf_mg_destroy(xf_trainer* tr) {
     fprintf(stderr, "    %-24s %8.4f\n", "total", tot);
   }
   cudaStreamSynchronize(mg->st2);
+  if (mg->p2p) {
+    // unmap the peers' buffers, then make sure every rank has done so before anybody frees its own
+    cudaStreamSynchronize(tr->table->stream);
+    for (int q = 0; q < mg->S; ++q)
+      for (int i = 0; i < XfMg::PEER_NBUF; ++i)
+        if (mg->peer[q][i]) cudaIpcCloseMemHandle(mg->peer[q][i]);
+    if (xf_mg_barrier(tr->comm, mg, tr->table->stream) == XF_OK) cudaStreamSynchronize(tr->table->stream);
+  }
+  if (mg->d_barrier) cudaFree(mg->d_barrier);
   for (int b = 0; b < 2; ++b) {
     XfDevBuf* pb[] = {&mg->d_set[b], &mg->d_keys[b], &mg->d_w[b], &mg->d_v[b], &mg->d_gw[b], &mg->d_acc[b],
                       &mg->grad_w[b], &mg->grad_v[b], &mg->bucket_cnt[b]};
@@ -445,9 +563,28 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
     XF_TRY(mg->rgrad_v.ensure(n_recv * 4 * K + 4));
   }
 
+  // peer-read offsets: what I own sits in bucket `rank` of every worker's bucket-major arrays; what I
+  // asked owner q for sits behind the requests of the lower ranks in q's response arrays
+  std::vector<uint64_t>& own_off = mg->own_off;
+  std::vector<uint64_t>& resp_off = mg->resp_off;
+  if (mg->p2p) {
+    for (int q = 0; q < S; ++q) {
+      own_off[q] = (uint64_t)mg->rank * ws.cap;
+      uint64_t o = 0;
+      for (int p = 0; p < mg->rank; ++p) o += mg->h_counts[p * S + q];
+      resp_off[q] = o;
+    }
+  }
+
   // ---- all-to-all #1: keys to their owners (the Pull request, kv_app.h:147-165)
   XF_MG_MARK(2);
-  XF_TRY(xf_all_to_all(c, ws.keys, mg->send_off, mg->send_cnt, mg->recv_keys.p, mg->recv_off, mg->recv_cnt, 8, 1, st));
+  if (mg->p2p) {
+    // every rank's dedup finished before its bucket sizes left (allgather above): read the keys in place
+    XF_TRY(xf_mg_pull(mg, cur ? XfMg::PEER_KEYS1 : XfMg::PEER_KEYS0, ws.keys, own_off, mg->recv_keys.p, mg->recv_off,
+                      mg->recv_cnt, 8, st));
+  } else {
+    XF_TRY(xf_all_to_all(c, ws.keys, mg->send_off, mg->send_cnt, mg->recv_keys.p, mg->recv_off, mg->recv_cnt, 8, 1, st));
+  }
   // ---- owner: Pull handler on this shard (insert-on-pull, ftrl.h:56,114-120)
   XF_MG_MARK(3);
   if (n_recv) {
@@ -463,8 +600,14 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
   }
   // ---- all-to-all #2: values back, straight into the work set (the Pull response)
   XF_MG_MARK(4);
-  XF_TRY(xf_all_to_all(c, mg->resp_w.p, mg->recv_off, mg->recv_cnt, ws.w, mg->send_off, mg->send_cnt, 4, 1, st));
-  if (K) XF_TRY(xf_all_to_all(c, mg->resp_v.p, mg->recv_off, mg->recv_cnt, ws.v, mg->send_off, mg->send_cnt, 4, K, st));
+  if (mg->p2p) {
+    XF_TRY(xf_mg_barrier(c, mg, st));  // every owner has answered
+    XF_TRY(xf_mg_pull(mg, XfMg::PEER_RESP_W, mg->resp_w.p, resp_off, ws.w, mg->send_off, mg->send_cnt, 4, st));
+    if (K) XF_TRY(xf_mg_pull(mg, XfMg::PEER_RESP_V, mg->resp_v.p, resp_off, ws.v, mg->send_off, mg->send_cnt, 4 * K, st));
+  } else {
+    XF_TRY(xf_all_to_all(c, mg->resp_w.p, mg->recv_off, mg->recv_cnt, ws.w, mg->send_off, mg->send_cnt, 4, 1, st));
+    if (K) XF_TRY(xf_all_to_all(c, mg->resp_v.p, mg->recv_off, mg->recv_cnt, ws.v, mg->send_off, mg->send_cnt, 4, K, st));
+  }
 
   // ---- worker: forward / residual / gradient accumulation against the work set
   XF_MG_MARK(5);
@@ -477,6 +620,8 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
   ++tr->launches;
   XF_MG_MARK(7);
   if (mode != 0) {
+    // peers may still be reading this rank's responses: nobody starts the next Pull before all are done
+    if (mg->p2p) XF_TRY(xf_mg_barrier(c, mg, st));
     XF_CUDA_TRY(cudaEventRecord(mg->ev_free[cur], st));
     XF_CUDA_TRY(cudaGetLastError());
     return XF_OK;  // forward only: nothing was accumulated
@@ -492,9 +637,18 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
 
   // ---- all-to-all #3: gradients to the owners (the Push, kv_app.h:110-118)
   XF_MG_MARK(8);
-  XF_TRY(xf_all_to_all(c, mg->grad_w[cur].p, mg->send_off, mg->send_cnt, mg->rgrad_w.p, mg->recv_off, mg->recv_cnt, 4, 1, st));
-  if (K)
-    XF_TRY(xf_all_to_all(c, mg->grad_v[cur].p, mg->send_off, mg->send_cnt, mg->rgrad_v.p, mg->recv_off, mg->recv_cnt, 4, K, st));
+  if (mg->p2p) {
+    XF_TRY(xf_mg_barrier(c, mg, st));  // every worker's gradients are final
+    XF_TRY(xf_mg_pull(mg, cur ? XfMg::PEER_GW1 : XfMg::PEER_GW0, mg->grad_w[cur].p, own_off, mg->rgrad_w.p, mg->recv_off,
+                      mg->recv_cnt, 4, st));
+    if (K)
+      XF_TRY(xf_mg_pull(mg, cur ? XfMg::PEER_GV1 : XfMg::PEER_GV0, mg->grad_v[cur].p, own_off, mg->rgrad_v.p, mg->recv_off,
+                        mg->recv_cnt, 4 * K, st));
+  } else {
+    XF_TRY(xf_all_to_all(c, mg->grad_w[cur].p, mg->send_off, mg->send_cnt, mg->rgrad_w.p, mg->recv_off, mg->recv_cnt, 4, 1, st));
+    if (K)
+      XF_TRY(xf_all_to_all(c, mg->grad_v[cur].p, mg->send_off, mg->send_cnt, mg->rgrad_v.p, mg->recv_off, mg->recv_cnt, 4, K, st));
+  }
   XF_CUDA_TRY(cudaEventRecord(mg->ev_free[cur], st));  // work set `cur` and its gradient buffers are free again
   // ---- owner: Push handler, one optimizer step per (source, key), sources in rank order
   XF_MG_MARK(9);
