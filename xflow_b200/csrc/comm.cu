@@ -18,8 +18,10 @@
 //           schedule of the reference's asynchronous multi-worker run (every worker pulled before any
 //           push of the round), reproducible by the oracle                [xf_k_update<.,false> x S]
 //
-// The three all-to-alls are grouped ncclSend/ncclRecv on the table's stream.  NVSwitch gives every
-// pair the same bandwidth, so a flat all-to-all is the right schedule; at S = 1 none of this runs.
+// The three all-to-alls are reads from peer memory (cudaIpc-mapped buffers + DMA copies behind a 4-byte
+// NCCL all-reduce, see xf_mg_setup_p2p / xf_mg_pull); grouped ncclSend/ncclRecv on the table's stream is
+// the fallback (XFLOW_P2P=0 or no IPC).  NVSwitch gives every pair the same bandwidth, so a flat
+// all-to-all is the right schedule; at S = 1 none of this runs.
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: the library itself is bound at run time, see XfNccl
 #include <stdio.h>
