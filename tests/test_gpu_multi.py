@@ -1,5 +1,5 @@
 """Multi-GPU parity (pytest -m gpu, needs >= 2 GPUs on the box; skipped otherwise): the sharded step of
-xflow_b200/csrc/comm.cu (NCCL all-to-all pull / push against a range-sharded device table), driven
+xflow_b200/csrc/comm.cu (all-to-all pull / push over peer memory or NCCL against a range-sharded device table), driven
 through the C ABI from one process per GPU, against the oracle's single-table lock-step schedule."""
 import os
 import socket
@@ -48,11 +48,15 @@ def _worker(rank, world, id_path, model, opt, K, ret):
         rp, keys, lab = _batch(rank, rnd)
         tr.step_host(rp, keys, lab)
         losses.append(tr.get_loss(B))
+    # forward only through the sharded path (same collective schedule on every rank), on a batch whose keys
+    # all exist already, so nothing changes in the table
+    rp, keys, lab = _batch(rank, ROUNDS - 1)
+    pctr = tr.predict_host(rp, keys)
     comm.barrier()
     allk = _all_keys(world)
     mine = np.array([A.shard_of(int(k), world) == rank for k in allk])
     ret[rank] = dict(keys=allk[mine], e=table.export(allk[mine]), losses=losses, size=table.size(),
-                     uniq=tr.stats()["unique_keys"])
+                     uniq=tr.stats()["unique_keys"], pctr=pctr)
     # foreign keys must be absent from this shard
     other = table.export(allk[~mine][:1000])
     assert not other["present"].any()
@@ -61,10 +65,15 @@ def _worker(rank, world, id_path, model, opt, K, ret):
     comm.close()
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("model,opt,K", [("lr", "ftrl", 0), ("fm", "ftrl", 8), ("fm", "sgd", 4)])
-def test_two_gpu_sharded_step_matches_lockstep_oracle(model, opt, K, tmp_path):
+def test_two_gpu_sharded_step_matches_lockstep_oracle(model, opt, K, exchange, tmp_path, monkeypatch):
+    """exchange = "peer": cudaIpc-mapped buffers read over NVLink (default); "nccl": grouped send/recv."""
     if api.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    if exchange == "nccl" and (model, opt) != ("fm", "ftrl"):
+        pytest.skip("the fallback exchange is checked on one configuration")
+    monkeypatch.setenv("XFLOW_P2P", "1" if exchange == "peer" else "0")  # inherited by the spawned ranks
     import torch.multiprocessing as mp
     world = 2
     gopt, oopt = (api.OPT_FTRL, O.OPT_FTRL) if opt == "ftrl" else (api.OPT_SGD, O.OPT_SGD)
@@ -99,3 +108,8 @@ def test_two_gpu_sharded_step_matches_lockstep_oracle(model, opt, K, tmp_path):
             assert_close(got["e"][k], ref[k], "rank %d %s" % (r, k))
         total += got["size"]
     assert total == t.size()
+    # predictions after training: the oracle's forward pass on the final table
+    for r in range(world):
+        rp, keys, lab = _batch(r, ROUNDS - 1)
+        _, _, _, loss = t.worker_compute(rp.astype(np.int64), keys, lab.astype(np.int32))
+        assert_close(ret[r]["pctr"], loss.astype(np.float64) + lab, "pctr rank %d" % r, abs_floor=1e-6)
