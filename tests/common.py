@@ -108,3 +108,65 @@ def oracle_case_run(case, syn_data, exact=False):
         O.train_file(t, train + "-00000", block, c["epochs"])
     lab, p = O.predict_file(t, test + "-00000", (4 << 20) if c["model"] == "lr" else (2 << 20))
     return t.export(g["keys"]), lab, p
+
+
+def check_fm_first_step(rp, keys, lab, K, v0_of, loss, export_of, alpha=0.05, beta=1.0, l1=5e-5, l2=10.0):
+    """Closed form of the FIRST FM + FTRL step on a fresh table (w = 0, n = z = 0, v = v0) in float64,
+    compared with an implementation's residuals and exported state.  Tolerances are noise-aware: a sum
+    over a key's occurrences is accepted within a few float32 ulps of the sum of the |terms| (both the
+    reference's sequential float sums and any other association of the same terms stay inside that).
+
+      v0_of(unique_keys) -> v0[U, K] float32      export_of(unique_keys) -> dict(zw, nw, v, nv, zv)
+      loss: the implementation's per-row residuals (float32, used as the exact input of the gradient)
+    Follows fm_worker.cc:126-202 (S, Q, residual, gw = K sum loss, gv = sum loss (S - v), / rows) and
+    ftrl.h:59-74.
+    """
+    B = lab.size
+    d = keys.size // B
+    assert keys.size == B * d and np.array_equal(np.diff(rp), np.full(B, d))
+    uk, inv = np.unique(keys, return_inverse=True)
+    v64 = v0_of(uk).astype(np.float64)
+    S = v64.sum(1)[inv].reshape(B, d).sum(1)
+    Q = (v64 ** 2).sum(1)[inv].reshape(B, d).sum(1)
+    ex = np.power(2.718281828, S * S - Q)  # Base::sigmoid; arguments stay far inside the clamps
+    loss = np.asarray(loss, np.float64)
+    assert_close(loss, ex / (1.0 + ex) - lab, "FM residual, step 1", rel=1e-5, abs_floor=1e-6)
+    occ_row = np.repeat(np.arange(B), d)
+    eps = 2.0 ** -23
+
+    def per_key(x):
+        out = np.zeros(uk.size)
+        np.add.at(out, inv, x[occ_row])
+        return out
+
+    L, Aq = per_key(loss), per_key(loss * S)
+    # noise scales: S itself is a float32 sum of d*K terms, so its error is relative to sum |v| of the row
+    Sabs = np.abs(v64).sum(1)[inv].reshape(B, d).sum(1)
+    magL, magA = per_key(np.abs(loss)), per_key(np.abs(loss) * Sabs)
+    e = export_of(uk)
+
+    def within(got, ref, tol, what):
+        bad = np.abs(np.asarray(got, np.float64) - ref) > tol
+        assert not bad.any(), "%s: %d/%d outside tolerance, worst %g vs tol %g" % (
+            what, int(bad.sum()), bad.size, float(np.abs(got - ref)[bad].max()), float(tol[bad].min()))
+
+    # w: g = K * L / B ; from the zero state n = g^2, z = g
+    gw = K * L / B
+    tol_gw = 1e-5 * np.abs(gw) + 8 * eps * K * magL / B + 1e-30
+    within(e["zw"], gw, tol_gw, "zw after step 1")
+    within(e["nw"], gw ** 2, 2 * np.abs(gw) * tol_gw + tol_gw ** 2 + 1e-5 * gw ** 2, "nw after step 1")
+    # v: g = (Aq - v L) / B ; n = g^2 ; z = g - |g| / alpha * v ; v' from (z, n)
+    g = (Aq[:, None] - v64 * L[:, None]) / B
+    tol_g = 1e-5 * np.abs(g) + 8 * eps * (magA[:, None] + np.abs(v64) * magL[:, None]) / B + 1e-30
+    z = g - np.abs(g) / alpha * v64
+    tol_z = tol_g * (1 + np.abs(v64) / alpha) + 1e-5 * np.abs(z)
+    within(e["nv"], g ** 2, 2 * np.abs(g) * tol_g + tol_g ** 2 + 1e-5 * g ** 2, "nv after step 1")
+    within(e["zv"], z, tol_z, "zv after step 1")
+    denom = (beta + np.abs(g)) / alpha + l2
+    vn = np.where(np.abs(z) <= l1, 0.0, (z - np.sign(z) * l1) / -denom)
+    decided = np.abs(np.abs(z) - l1) > 2 * tol_z  # at the L1 threshold the last bit decides
+    tol_v = tol_z / denom + 1e-5 * np.abs(vn) + 1e-30
+    got_v = np.asarray(e["v"], np.float64)
+    bad = decided & (np.abs(got_v - vn) > tol_v)
+    assert not bad.any(), "v after step 1: %d/%d outside tolerance" % (int(bad.sum()), bad.size)
+    return uk, e

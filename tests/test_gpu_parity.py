@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from cases import CASES
-from common import assert_close, assert_close_noise_aware, data_prefixes, golden, oracle_case_run
+from common import check_fm_first_step, assert_close, assert_close_noise_aware, data_prefixes, golden, oracle_case_run
 from oracle import oracle as O
 from xflow_b200 import api, datagen
 
@@ -272,53 +272,28 @@ def test_full_size_batch_properties():
 
 
 def test_full_size_fm_batch_properties():
-    """cfg5 shape (B = 65536, 64 nnz/row, Zipf(1.05) ids in 1e8, K = 16, FTRL): the first step in closed form.
+    """cfg5 shape (B = 65536, 64 nnz/row, Zipf(1.05) ids in 1e8, K = 16, FTRL): the first step in closed form
+    (common.check_fm_first_step, float64 numpy; the CPU suite pins the same checker to the oracle).
     Exercises the hot-key path (one key holds ~8 % of the tokens) and the factorised latent gradient
-    gv = Aq - v L at full size, against float64 numpy."""
+    gv = Aq - v L at full size."""
     B, d, space, K = 65536, 64, 10 ** 8, 16
-    alpha, beta, l1, l2 = 0.05, 1.0, 5e-5, 10.0
     gt = api.Table(latent_dim=K, capacity=1 << 23, v_init=api.VINIT_COUNTER, seed=3)
     tr = api.Trainer(gt, model=api.MODEL_FM, max_rows=B, max_nnz=B * d, keep_loss=True)
     rp, keys, lab = datagen.make_csr_keys(2, B, d, space, api.hash_decimal_ids, dist="zipf")
-    uk, inv, cnt = np.unique(keys, return_inverse=True, return_counts=True)
+    uk, cnt = np.unique(keys, return_counts=True)
     assert cnt.max() > 0.03 * keys.size          # there is a genuinely hot key
     w0, v0 = gt.pull(uk)                         # insert-on-pull; v = counter-based initial values
     assert not w0.any() and gt.size() == uk.size
     tr.step_host(rp, keys, lab)
-    loss = tr.get_loss(B).astype(np.float64)
-    v64 = v0.astype(np.float64)
-    S = v64.sum(1)[inv].reshape(B, d).sum(1)
-    Q = (v64 ** 2).sum(1)[inv].reshape(B, d).sum(1)
-    ex = np.power(2.718281828, S * S - Q)        # Base::sigmoid, no clamping needed at these magnitudes
-    assert_close(loss, ex / (1.0 + ex) - lab, "FM residual, step 1", rel=1e-5, abs_floor=1e-6)
+    loss = tr.get_loss(B)
     assert tr.stats()["unique_keys"] == uk.size == gt.size()
-    # per-key sums over occurrences
-    occ_row = np.repeat(np.arange(B), d)
-    L = np.zeros(uk.size)
-    Aq = np.zeros(uk.size)
-    np.add.at(L, inv, loss[occ_row])
-    np.add.at(Aq, inv, (loss * S)[occ_row])
-    e = gt.export(uk)
-    # w: gradient K * L / B (fm_worker.cc:140), first FTRL step from zero state: n = g^2, z = g
-    gw = (K * L / B).astype(np.float32).astype(np.float64)
-    assert_close(e["zw"], gw, "zw after step 1", rel=1e-5, abs_floor=1e-12)
-    assert_close(e["nw"], gw ** 2, "nw after step 1", rel=2e-5, abs_floor=1e-20)
-    # v: g = (Aq - v L) / B ; n = g^2 ; z = g - |g| / alpha * v ; v' from (z, n)
-    g = ((Aq[:, None] - v64 * L[:, None]) / B).astype(np.float32).astype(np.float64)
-    z = g - np.abs(g) / alpha * v64
-    assert_close(e["nv"], g ** 2, "nv after step 1", rel=4e-5, abs_floor=1e-20)
-    assert_close(e["zv"], z, "zv after step 1", rel=2e-5, abs_floor=1e-12)
-    vn = np.where(np.abs(z) <= l1, 0.0, (z - np.sign(z) * l1) / -((beta + np.abs(g)) / alpha + l2))
-    near = np.abs(np.abs(z) - l1) < 1e-8         # the L1 threshold decides by the last bit there
-    assert_close(e["v"][~near], vn[~near], "v after step 1", rel=2e-5, abs_floor=1e-9)
-    # token order inside rows changes nothing
+    _, e = check_fm_first_step(rp, keys, lab, K, lambda k: v0, loss, gt.export)
+    # token order inside rows changes nothing (beyond the float32 rounding of the row sums)
     gt2 = api.Table(latent_dim=K, capacity=1 << 23, v_init=api.VINIT_COUNTER, seed=3)
-    tr2 = api.Trainer(gt2, model=api.MODEL_FM, max_rows=B, max_nnz=B * d)
+    tr2 = api.Trainer(gt2, model=api.MODEL_FM, max_rows=B, max_nnz=B * d, keep_loss=True)
     perm = np.arange(keys.size).reshape(B, d)[:, ::-1].reshape(-1)
     tr2.step_host(rp, keys[perm], lab)
-    e2 = gt2.export(uk)
-    assert_close(e2["zv"], e["zv"], "zv under token permutation", rel=2e-5, abs_floor=1e-9)
-    assert_close(e2["zw"], e["zw"], "zw under token permutation", rel=1e-5, abs_floor=1e-12)
+    check_fm_first_step(rp, keys[perm], lab, K, lambda k: v0, tr2.get_loss(B), gt2.export)
 
 
 def test_device_id_hashing_is_bit_exact_and_ids_path_trains_identically():
