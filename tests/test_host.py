@@ -148,3 +148,43 @@ def test_loader_large_blocks_read_in_parallel_pieces(tmp_path):
             assert np.array_equal(a, b)
     assert np.array_equal(small[0], api.hash_decimal_ids(ids))
     assert np.array_equal(small[1], lab)
+
+
+def _parse_block_py(text):
+    """The reference's row / token rules (load_data_from_disk.cc:126-209) in plain Python."""
+    rows = []
+    for line in text.split(b"\n"):
+        if not line:
+            continue
+        label, _, rest = line.partition(b"\t")
+        try:
+            y = 1 if np.float32(float(label.strip() or b"0")) > 1e-7 else 0
+        except ValueError:
+            y = 0
+        toks = [t for t in rest.replace(b"\r", b"").split(b" ") if t]
+        rows.append((y, [api.hash_bytes(t.split(b":")[1]) for t in toks]))
+    return rows
+
+
+@pytest.mark.parametrize("block_bytes", [4096, 1 << 16, 1 << 22])
+def test_raw_blocks_are_the_parsed_blocks(block_bytes):
+    """xf_loader_next_raw (block formation only, what the device parser is fed) cuts the file exactly where
+    xf_loader_next does: parsing each raw block in Python gives the rows of the corresponding CSR block."""
+    path = os.path.join(GOLDEN, "data", "small_train-00000")
+    parsed = list(api.Loader(path, block_bytes))
+    raw = []
+    ld = api.Loader(path, block_bytes)
+    while True:
+        t = ld.next_raw()
+        if not t:
+            break
+        raw.append(t)
+    assert len(raw) == len(parsed)
+    for text, (rp, keys, lab) in zip(raw, parsed):
+        rows = _parse_block_py(text)
+        assert [y for y, _ in rows] == lab.tolist()
+        assert [len(k) for _, k in rows] == np.diff(rp).tolist()
+        assert [h for _, k in rows for h in k] == keys.tolist()
+    # every byte of the file is in exactly one block (up to the newline at each cut)
+    whole = open(path, "rb").read()
+    assert b"".join(r.rstrip(b"\n") for r in raw).replace(b"\n", b"") == whole.replace(b"\n", b"")

@@ -34,20 +34,6 @@ __device__ __forceinline__ void xf_ldv_step(const float* p, float (&o)[VEC]) {
   else if (VEC == 2) { float2 t = __ldca(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1 % VEC] = t.y; }
   else { o[0] = __ldca(p); }
 }
-// vector reduction (no return value) into global memory: one L2 atomic transaction per 8 / 16 bytes
-template <int VEC>
-__device__ __forceinline__ void xf_redv_step(float* p, const float (&o)[VEC]) {
-  if (VEC == 4) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(o[0]), "f"(o[1 % VEC]),
-                 "f"(o[2 % VEC]), "f"(o[3 % VEC])
-                 : "memory");
-  } else if (VEC == 2) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(o[0]), "f"(o[1 % VEC]) : "memory");
-  } else {
-    atomicAdd(p, o[0]);
-  }
-}
-
 // FM: (sum_k v, sum_k v^2) of one token's latent row  (fm_worker.cc:178-192, per-token part)
 template <int VEC>
 __device__ __forceinline__ void xf_fm_token(const XfTableView& t, uint32_t slot, uint32_t flags, uint64_t key,
