@@ -96,6 +96,7 @@ class XF_CXX_API WorkerBase {
   const char* model_name() const { return model_ == XF_MODEL_LR ? "LR" : "FM"; }
   void ensure_trainer(uint32_t rows, uint32_t nnz);
   void ensure_trainer_for_block(uint64_t bytes);
+  void ingest_block(const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz);
 
   int model_;
   std::string train_file_path, test_file_path;

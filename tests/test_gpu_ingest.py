@@ -200,3 +200,26 @@ def test_text_model_dump(tmp_path, K):
             gv = np.array([[float(x) for x in g[2].split(" ")] for g in got], np.float32)
             assert np.array_equal(gv, v[keep])
     t.close()
+
+
+def test_cli_blocks_with_featureless_rows(tmp_path):
+    """Rows without features ("1\\t\\n", 3 bytes) put more rows into a block than the worker sized its
+    trainer for (8 bytes per well-formed row): the worker re-sizes and parses again.  Same output as the
+    host parser."""
+    exe = os.path.join(ROOT, "xflow_b200", "bin", "xflow_lr")
+    body = open(TRAIN, "rb").read()
+    train = tmp_path / "sparse-00000"
+    train.write_bytes(b"1\t\n" * 400000 + body + b"0\t\n" * 30000)  # first 1 MiB block: ~350 k rows
+    test = tmp_path / "t-00000"
+    test.write_bytes(b"0\t\n" * 5000 + open(TEST, "rb").read())
+    outs = []
+    for host_parse in ("0", "1"):
+        d = tmp_path / ("hp" + host_parse)
+        d.mkdir()
+        env = dict(os.environ, XFLOW_HOST_PARSE=host_parse, XFLOW_BLOCK_MB="1")
+        r = subprocess.run([exe, str(tmp_path / "sparse"), str(tmp_path / "t"), "0", "2"], cwd=str(d), env=env,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(((d / "pred_0_0.txt").read_text(), [l for l in r.stdout.splitlines() if "logloss" in l]))
+    assert outs[0][1] and outs[0] == outs[1]
+    assert outs[0][0].count("\n") == 5000 + 200

@@ -155,9 +155,21 @@ void WorkerBase::update(int start, int end) {
   rows_trained += rows;
 }
 
-// a text block of `bytes` bytes holds at most bytes/8 rows ("0\ta:b:c\n") and bytes/6 tokens ("a:b:c ")
+// a well-formed text block of `bytes` bytes holds at most bytes/8 rows ("0\ta:b:c\n") and bytes/6 tokens
+// ("a:b:c ")
 void WorkerBase::ensure_trainer_for_block(uint64_t bytes) {
   ensure_trainer((uint32_t)(bytes / 8 + 2), (uint32_t)(bytes / 6 + 2));
+}
+
+// parse one raw block on the device; a block with rows that carry no features ("0\n") can hold more rows
+// than ensure_trainer_for_block assumed: size the trainer for the absolute worst case and try once more
+void WorkerBase::ingest_block(const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz) {
+  int rc = xf_trainer_ingest_text(trainer_, text, len, rows, nnz);
+  if (rc == XF_ERR_ARG && (trainer_rows_ < len / 2 + 2 || trainer_nnz_ < len / 4 + 2)) {
+    ensure_trainer((uint32_t)(len / 2 + 2), (uint32_t)(len / 4 + 2));
+    rc = xf_trainer_ingest_text(trainer_, text, len, rows, nnz);
+  }
+  must(rc, "xf_trainer_ingest_text");
 }
 
 void WorkerBase::batch_training() {
@@ -176,7 +188,7 @@ void WorkerBase::batch_training() {
       must(xf_loader_next_raw(loader, &text, &len), "xf_loader_next_raw");
       if (len == 0) break;
       uint32_t rows = 0, nnz = 0;
-      must(xf_trainer_ingest_text(trainer_, text, len, &rows, &nnz), "xf_trainer_ingest_text");
+      ingest_block(text, len, &rows, &nnz);
       if (rows == 0) break;  // :189
       const uint32_t thread_size = rows / (uint32_t)core_num;  // :190 — remainder rows are dropped, as in the reference
       for (uint32_t i = 0; i < (uint32_t)core_num; ++i) {      // :192-196
@@ -249,7 +261,7 @@ void WorkerBase::predict(int rank_arg, int block) {
     must(xf_loader_next_raw(loader, &text, &len), "xf_loader_next_raw");
     if (len == 0) break;
     uint32_t rows = 0, nnz = 0;
-    must(xf_trainer_ingest_text(trainer_, text, len, &rows, &nnz), "xf_trainer_ingest_text");
+    ingest_block(text, len, &rows, &nnz);
     if (rows == 0) break;
     const uint32_t thread_size = rows / (uint32_t)core_num;
     pctr_buf.resize(thread_size);
