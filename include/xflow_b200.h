@@ -243,6 +243,14 @@ XF_DLL int xf_comm_get_id(uint8_t id[XF_COMM_ID_BYTES]);
 XF_DLL int xf_comm_create(xf_comm** out, const uint8_t id[XF_COMM_ID_BYTES], int rank, int nranks, int device);
 XF_DLL int xf_comm_destroy(xf_comm* c);
 XF_DLL int xf_comm_barrier(xf_comm* c);
+/* Host-side plan of the sharded step's three exchanges (comm.cu), a pure function exposed for tests:
+ * counts[p*S+q] = unique keys of worker p's batch owned by shard q; offsets in keys, bucket stride `cap`.
+ * send_* : my bucket q (request / push to owner q, its answers land there); recv_* : source q's segment of my
+ * owner-side arrays; own_off[q] : my share inside worker q's arrays; resp_off[q] : my answers inside owner
+ * q's response arrays.  All outputs are arrays of S elements. */
+XF_DLL int xf_exchange_plan(const uint32_t* counts, int S, int rank, uint64_t cap, uint64_t* send_off,
+                            uint64_t* send_cnt, uint64_t* recv_off, uint64_t* recv_cnt, uint64_t* own_off,
+                            uint64_t* resp_off);
 
 /* ------------------------------------------------------------------------------------------------
  * 1. Reference C API (src/c_api/c_api.h:26-29), unchanged signatures.

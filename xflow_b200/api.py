@@ -95,6 +95,7 @@ SIGNATURES = {
     "xf_comm_create": (_i, [_vp, _vp, _i, _i, _i]),
     "xf_comm_destroy": (_i, [_vp]),
     "xf_comm_barrier": (_i, [_vp]),
+    "xf_exchange_plan": (_i, [_vp, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "XFCreate": (_i, [_vp, C.c_char_p, C.c_char_p]),
     "XFStartTrain": (_i, [_vp]),
     "XFCreateEx": (_i, [_vp, C.c_char_p, C.c_char_p, _i, _i, _i, _i]),
@@ -302,6 +303,16 @@ class Table:
 
     def sync(self):
         _check(lib().xf_table_sync(self.h))
+
+
+def exchange_plan(counts, rank, cap):
+    """comm.cu's exchange plan for `rank`: dict of S-element offset / count arrays (see xflow_b200.h)."""
+    counts = np.ascontiguousarray(counts, np.uint32)
+    S = counts.shape[0]
+    names = ("send_off", "send_cnt", "recv_off", "recv_cnt", "own_off", "resp_off")
+    out = {n: np.zeros(S, np.uint64) for n in names}
+    _check(lib().xf_exchange_plan(_p(counts), S, rank, cap, *[_p(out[n]) for n in names]))
+    return out
 
 
 class Comm:

@@ -504,6 +504,34 @@ static int xf_all_to_all(xf_comm* c, const void* send, const std::vector<uint64_
   return XF_OK;
 }
 
+// Where everything of one step's three exchanges lives, from the S x S matrix counts[p*S+q] = number of
+// unique keys of worker p's batch owned by q (every rank holds the whole matrix after the allgather).
+// Element offsets ("keys"); all bucket-major arrays of a worker have bucket stride `cap`.
+//   send_off/send_cnt[q]  my bucket q: what I request from / push to owner q (and where its answers land)
+//   recv_off/recv_cnt[q]  where source q's keys / gradients land in my owner-side arrays (grouped by source)
+//   own_off[q]            where my share starts inside WORKER q's arrays   (peer reads of keys and gradients)
+//   resp_off[q]           where my answers start inside OWNER q's response arrays (peer reads of values)
+XF_DLL int xf_exchange_plan(const uint32_t* counts, int S, int rank, uint64_t cap, uint64_t* send_off,
+                            uint64_t* send_cnt, uint64_t* recv_off, uint64_t* recv_cnt, uint64_t* own_off,
+                            uint64_t* resp_off) {
+  if (!counts || S < 1 || rank < 0 || rank >= S || !send_off || !send_cnt || !recv_off || !recv_cnt || !own_off ||
+      !resp_off)
+    return XF_ERR_ARG;
+  uint64_t n_recv = 0;
+  for (int q = 0; q < S; ++q) {
+    send_cnt[q] = counts[rank * S + q];  // my keys owned by q
+    recv_cnt[q] = counts[q * S + rank];  // q's keys owned by me
+    send_off[q] = (uint64_t)q * cap;     // bucket-major work-set arrays
+    recv_off[q] = n_recv;
+    n_recv += recv_cnt[q];
+    own_off[q] = (uint64_t)rank * cap;   // bucket `rank` of worker q
+    uint64_t before = 0;                 // owner q answers its sources in rank order
+    for (int p = 0; p < rank; ++p) before += counts[p * S + q];
+    resp_off[q] = before;
+  }
+  return XF_OK;
+}
+
 int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys, const uint8_t* d_labels,
                uint32_t rows, uint32_t nnz, int mode, float* d_abs, cudaEvent_t* pm) {
   XfMg* mg = (XfMg*)tr->mg;
@@ -542,15 +570,13 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
   XF_NCCL_TRY(g_nccl.AllGather(mg->bucket_cnt[cur].p, mg->all_counts.p, (size_t)S, ncclUint32, cd, sd));
   XF_CUDA_TRY(cudaMemcpyAsync(mg->h_counts, mg->all_counts.p, (size_t)S * S * 4, cudaMemcpyDeviceToHost, sd));
   XF_CUDA_TRY(cudaStreamSynchronize(sd));
+  XF_TRY(xf_exchange_plan(mg->h_counts, S, mg->rank, ws.cap, mg->send_off.data(), mg->send_cnt.data(), mg->recv_off.data(),
+                          mg->recv_cnt.data(), mg->own_off.data(), mg->resp_off.data()));
   uint64_t n_send = 0, n_recv = 0;
   XfBucketCounts bc;
   memset(&bc, 0, sizeof(bc));
   uint32_t max_bucket = 0;
   for (int q = 0; q < S; ++q) {
-    mg->send_cnt[q] = mg->h_counts[mg->rank * S + q];   // my keys owned by q
-    mg->recv_cnt[q] = mg->h_counts[q * S + mg->rank];   // q's keys owned by me
-    mg->send_off[q] = (uint64_t)q * ws.cap;             // bucket-major work-set arrays
-    mg->recv_off[q] = n_recv;
     bc.c[q] = (uint32_t)mg->send_cnt[q];
     if (bc.c[q] > max_bucket) max_bucket = bc.c[q];
     n_send += mg->send_cnt[q];
@@ -565,18 +591,8 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
     XF_TRY(mg->rgrad_v.ensure(n_recv * 4 * K + 4));
   }
 
-  // peer-read offsets: what I own sits in bucket `rank` of every worker's bucket-major arrays; what I
-  // asked owner q for sits behind the requests of the lower ranks in q's response arrays
   std::vector<uint64_t>& own_off = mg->own_off;
   std::vector<uint64_t>& resp_off = mg->resp_off;
-  if (mg->p2p) {
-    for (int q = 0; q < S; ++q) {
-      own_off[q] = (uint64_t)mg->rank * ws.cap;
-      uint64_t o = 0;
-      for (int p = 0; p < mg->rank; ++p) o += mg->h_counts[p * S + q];
-      resp_off[q] = o;
-    }
-  }
 
   // ---- all-to-all #1: keys to their owners (the Pull request, kv_app.h:147-165)
   XF_MG_MARK(2);
