@@ -153,6 +153,17 @@ def cpu_reference_rate(wl, rows, steps, warmup):
         used = cores
         how = "oracle/_ref/xflow_ref = the reference's src/ compiled unmodified (-O2) + in-process ps shim " \
               "(zero transport cost), core_num=%d" % cores
+        # SURVEY 8d also asks for the single-thread figure: same binary, core_num=1, a quarter of the rows
+        single = None
+        try:
+            rows1 = max(1024, rows // 4)
+            train1 = os.path.join(tmp, "train1")
+            datagen.write_text(train1 + "-00000", rp[:rows1 + 1], ids[:int(rp[rows1])], lab[:rows1])
+            r1 = O.run_ref(wl["model"], wl["opt"], train1, os.path.join(tmp, "empty"), 1, tmp, core=1,
+                           block_mb=size_mb, vdim=wl["K"] or 10, no_predict=True)
+            single = {"value": rows1 / r1["train_seconds"], "unit": "examples/s", "cores": 1, "rows": rows1}
+        except Exception as ex:  # informational only
+            single = {"value": None, "error": repr(ex)}
     else:
         kind = "port"
         O.build()
@@ -165,7 +176,7 @@ def cpu_reference_rate(wl, rows, steps, warmup):
         used = 1
         how = "oracle/xflow_oracle.cc (scalar port), 1 thread"
     mean_t = float(np.mean(times))
-    desc = {"kind": kind, "cores": used,
+    desc = {"kind": kind, "cores": used, "single_core": single if kind == "reference" else None,
             "sample": "%d rows x %d nnz of the same workload per step (text parse + update(), 1 epoch, empty "
                       "table); %s" % (rows, wl["nnz"], how)}
     return rows / mean_t, mean_t, desc
