@@ -930,6 +930,7 @@ XF_DLL int xf_trainer_step_host_ids_async(xf_trainer* tr, const uint32_t* row_pt
 
 XF_DLL int xf_trainer_ingest_text(xf_trainer* tr, const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz) {
   if (!tr || (!text && len) || !rows || !nnz) return XF_ERR_ARG;
+  if (len >= 0xFFFFFFF0ull) { xf_set_error("ingest: a block must be smaller than 4 GiB (u32 token offsets)"); return XF_ERR_ARG; }
   XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
   cudaStream_t st = tr->table->stream;
   // upper bounds for a block of `len` bytes: shortest row "0\ta:b:c\n" = 8 bytes, shortest extra token 6 bytes
