@@ -166,6 +166,34 @@ def _parse_block_py(text):
     return rows
 
 
+def _parse_block_device_rules(t):
+    """The per-byte rules of the device parser (ingest.cu: xf_is_line_start / xf_is_tok_start / label up to
+    the tab / fid between the first two colons), restated byte by byte."""
+    n, rows = len(t), []
+    for p in range(n):
+        c = t[p:p + 1]
+        if (p == 0 or t[p - 1:p] == b"\n") and c != b"\n":
+            q = p
+            while q < n and t[q:q + 1] not in (b"\t", b"\n"):
+                q += 1
+            try:
+                y = 1 if np.float32(float(t[p:q].strip() or b"0")) > 1e-7 else 0
+            except ValueError:
+                y = 0
+            rows.append((y, []))
+        if p > 0 and t[p - 1:p] in (b" ", b"\t") and c not in (b" ", b"\n", b"\t", b"\r"):
+            q, colons = p, []
+            while q < n and t[q:q + 1] not in (b" ", b"\n"):
+                if t[q:q + 1] == b":":
+                    colons.append(q)
+                    if len(colons) == 2:
+                        break
+                q += 1
+            assert len(colons) == 2
+            rows[-1][1].append(api.hash_bytes(t[colons[0] + 1:colons[1]]))
+    return rows
+
+
 @pytest.mark.parametrize("block_bytes", [4096, 1 << 16, 1 << 22])
 def test_raw_blocks_are_the_parsed_blocks(block_bytes):
     """xf_loader_next_raw (block formation only, what the device parser is fed) cuts the file exactly where
@@ -226,3 +254,41 @@ def test_exchange_plan_moves_every_key_to_its_owner_and_back(S):
             got[q * cap:q * cap + n] = resp[q][int(pl["resp_off"][q]):int(pl["resp_off"][q]) + n]
         live = req[r] >= 0
         assert np.array_equal(got[live], req[r][live] + 1) and (got[~live] == -3).all()
+
+
+def test_loader_fuzz_against_python_parser(tmp_path):
+    """Random well-formed shards (random labels incl. floats, 0..6 tokens per row, fids of random bytes and
+    lengths, CRLF or LF, with / without final newline) cut at random block sizes: the rows, labels and
+    hashes of xf_loader_next equal a plain-Python parse of the whole file."""
+    from hypothesis import given, settings, strategies as st
+    alphabet = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789_-."
+    fid = st.text(alphabet=alphabet, min_size=1, max_size=24)
+    tok = st.builds(lambda f, i, v: "%d:%s:%s" % (f, i, v), st.integers(0, 40), fid,
+                    st.sampled_from(["1", "0.5", "3", "1e-3"]))
+    label = st.sampled_from(["0", "1", "1.0", "0.0", "0.25", "-1", "1e-9", "2e-7"])
+    row = st.tuples(label, st.lists(tok, min_size=0, max_size=6))
+    path = str(tmp_path / "fuzz-00000")
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(row, min_size=1, max_size=60), st.booleans(), st.booleans(), st.integers(64, 2048))
+    def check(rows, crlf, final_newline, block_bytes):
+        eol = "\r\n" if crlf else "\n"
+        text = eol.join("%s\t%s" % (l, " ".join(t)) for l, t in rows) + (eol if final_newline else "")
+        data = text.encode()
+        longest = max(len(x) for x in data.split(b"\n")) + 2
+        if block_bytes <= longest:       # a block must be able to hold the longest row (as in the reference)
+            block_bytes = longest + 1
+        with open(path, "wb") as f:
+            f.write(data)
+        want = _parse_block_py(data)
+        assert _parse_block_device_rules(data) == want      # host and device parsers implement one rule set
+        got_y, got_len, got_k = [], [], []
+        for rp, keys, lab in api.Loader(path, block_bytes):
+            got_y += lab.tolist()
+            got_len += np.diff(rp).tolist()
+            got_k += keys.tolist()
+        assert got_y == [y for y, _ in want]
+        assert got_len == [len(k) for _, k in want]
+        assert got_k == [h for _, k in want for h in k]
+
+    check()

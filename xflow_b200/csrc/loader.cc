@@ -242,7 +242,9 @@ XF_DLL int xf_loader_next(xf_loader* l, uint32_t* rows_out, uint32_t* nnz_out) {
           else if (!c2) c2 = q;
         }
       }
-      if (q > p) {
+      // a token that starts with '\r' is the CR of a CRLF row without features, not a feature (the device
+      // parser in ingest.cu applies the same rule)
+      if (q > p && *p != '\r') {
         if (!c1 || !c2) { xf_set_error("loader: token without three ':'-separated fields"); return XF_ERR_IO; }
         if (nnz >= l->max_tok) { xf_set_error("loader: token capacity exceeded"); return XF_ERR_IO; }
         l->keys[nnz++] = xf_murmur64a(c1 + 1, (uint64_t)(c2 - c1 - 1));
