@@ -142,7 +142,7 @@ static size_t xf_read_block(xf_loader* l, char* dst, size_t n) {
   if (n == 0) return 0;
   const size_t kMinPerThread = (size_t)2 << 20;
   unsigned hw = std::thread::hardware_concurrency();
-  size_t nthreads = std::min<size_t>(std::min<size_t>(8, hw ? hw : 1), n / kMinPerThread);
+  size_t nthreads = std::min<size_t>(std::min<size_t>(16, hw ? hw : 1), n / kMinPerThread);
   if (nthreads < 1) nthreads = 1;
   std::vector<size_t> got(nthreads, 0);
   auto work = [&](size_t t) {
