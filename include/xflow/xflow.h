@@ -7,7 +7,8 @@
 //   xflow::FMWorker         src/model/fm/fm_worker.h:31-95
 //   xflow::w_dim, v_dim, alpha, beta, lambda1, lambda2   src/optimizer/ftrl.h:15-20
 //   xflow::learning_rate                                  src/optimizer/sgd.h:16
-//   xflow::FTRL / xflow::SGD handle tags                  src/optimizer/ftrl.h:38,98 ; sgd.h:30,74
+//   xflow::FTRL::KVServerFTRLHandle_w/_v, xflow::SGD::KVServerSGDHandle_w/_v and the ps::KVServer /
+//   ps::KVWorker surface they plug into live in ps_compat.h  (src/optimizer/ftrl.h:38,98 ; sgd.h:30,74)
 // so that src/model/main.cc compiles against this header unchanged in shape:
 //     if (server role) new xflow::Server();  ...  xflow::LRWorker w(train, test); w.epochs = N; w.train();
 //

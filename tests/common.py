@@ -170,3 +170,17 @@ def check_fm_first_step(rp, keys, lab, K, v0_of, loss, export_of, alpha=0.05, be
     bad = decided & (np.abs(got_v - vn) > tol_v)
     assert not bad.any(), "v after step 1: %d/%d outside tolerance" % (int(bad.sum()), bad.size)
     return uk, e
+
+
+def build_and_run_ps_compat(tmp_dir):
+    """Compile tests/cxx/ps_compat_check.cc against the shipped headers + library and run it."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(str(tmp_dir), "ps_compat_check")
+    libdir = os.path.join(root, "xflow_b200", "lib")
+    r = subprocess.run(["g++", "-std=c++14", "-Wall", "-Wextra", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "cxx", "ps_compat_check.cc"), "-o", exe, "-L", libdir,
+                        "-lxflow_b200", "-Wl,-rpath," + libdir, "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "warning" not in r.stderr, r.stderr
+    return subprocess.run([exe], capture_output=True, text=True, timeout=120)

@@ -95,3 +95,12 @@ def test_cli_slices_drop_remainder_like_reference(tmp_path):
     assert tp + fp == lab.size == 196
     assert abs(ll - m["logloss"]) <= 2e-5 * abs(m["logloss"]) + 1e-6
     assert abs(auc - m["auc"]) <= 2e-5
+
+
+def test_ps_lite_shaped_surface_on_the_device(tmp_path):
+    """include/xflow/ps_compat.h: ps::KVWorker Push / Pull through the reference's optimizer functors
+    (FTRL::KVServerFTRLHandle_w / _v installed on ps::KVServer 0 / 1, server.h:22-31) against the device table:
+    insert-on-pull, the first FTRL step in closed form, size checks, optimizer mismatch (tests/cxx)."""
+    from common import build_and_run_ps_compat
+    r = build_and_run_ps_compat(tmp_path)
+    assert r.returncode == 0 and "transport ok" in r.stdout and "device handles ok" in r.stdout, r.stdout + r.stderr

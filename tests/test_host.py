@@ -292,3 +292,17 @@ def test_loader_fuzz_against_python_parser(tmp_path):
         assert got_k == [h for _, k in want for h in k]
 
     check()
+
+
+def test_ps_compat_header(tmp_path):
+    """include/xflow/ps_compat.h (ps::KVServer / KVWorker / KVPairs / KVMeta and the reference's four optimizer
+    functors over the device table): compiles as plain C++14 against the shipped library, its in-process
+    transport behaves like ps-lite's request / response contract, and the device handles fail loudly when
+    there is no GPU (on a GPU box the same program checks the first FTRL step through Push / Pull)."""
+    from common import build_and_run_ps_compat
+    r = build_and_run_ps_compat(tmp_path)
+    assert "transport ok" in r.stdout, r.stdout + r.stderr
+    if api.device_count() > 0:
+        assert r.returncode == 0 and "device handles ok" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "failed loudly" in r.stdout, r.stdout + r.stderr
