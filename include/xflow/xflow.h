@@ -26,6 +26,7 @@
 #include <stdint.h>
 
 #include <fstream>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,11 @@ class XF_CXX_API Server {
   xf_table* table_fm();   // K = v_dim table (created on first use)
   Optimizer optimizer() const { return opt_; }
   int device() const { return device_; }
+  // XFLOW_WORLD / WORLD_SIZE > 1: this process is worker `rank()` of `world()` and owns key range `rank()`
+  // (postoffice.cc:134-143); comm() is the exchange the sharded trainers use (nullptr when alone)
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  xf_comm* comm() const { return comm_; }
   // the process-wide server the workers attach to (created with defaults if none exists)
   static Server* Get();
 
@@ -64,6 +70,8 @@ class XF_CXX_API Server {
   Optimizer opt_;
   int latent_dim_;
   int device_;
+  int rank_ = 0, world_ = 1;
+  xf_comm* comm_ = nullptr;
   xf_table* lr_ = nullptr;
   xf_table* fm_ = nullptr;
 };
@@ -98,12 +106,19 @@ class XF_CXX_API WorkerBase {
   void ensure_trainer(uint32_t rows, uint32_t nnz);
   void ensure_trainer_for_block(uint64_t bytes);
   void ingest_block(const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz);
+  void open_loader(const char* path, uint64_t block_bytes);
+  uint64_t count_blocks(const char* path, uint64_t block_bytes);
+  void run_blocks(uint64_t collective_blocks, const std::function<void(uint32_t rows)>& on_block);
 
   int model_;
   std::string train_file_path, test_file_path;
   char train_data_path[1024];
   char test_data_path[1024];
   xf_table* table_ = nullptr;
+  xf_comm* comm_ = nullptr;       // non-null: the sharded (multi-GPU) step; core_num is then 1
+  xf_loader* loader_ = nullptr;   // one loader for every epoch of a file
+  std::string loader_path_;
+  uint64_t loader_block_ = 0;
   xf_trainer* trainer_ = nullptr;
   uint32_t trainer_rows_ = 0, trainer_nnz_ = 0;
   // current block (valid inside batch_training / predict)
@@ -125,8 +140,10 @@ class XF_CXX_API FMWorker : public WorkerBase {
   FMWorker(const char* train_file, const char* test_file);
 };
 
-// what a ps-lite process would ask its environment (ps.h): single-box, one process per GPU
+// what a ps-lite process would ask its environment (ps.h): single-box, one process per GPU.
+// XFLOW_RANK (or RANK) and XFLOW_WORLD (or WORLD_SIZE); XFLOW_DEVICE / LOCAL_RANK pick the GPU.
 XF_CXX_API int MyRank();
+XF_CXX_API int NumWorkers();
 
 }  // namespace xflow
 

@@ -110,6 +110,11 @@ XF_DLL int xf_table_capacity(xf_table* t, uint64_t* n_slots);
 XF_DLL int xf_table_row_bytes(xf_table* t, uint32_t* bytes);
 /* make room for at least n_keys keys at load factor <= 0.5 (rehashes on device if needed) */
 XF_DLL int xf_table_reserve(xf_table* t, uint64_t n_keys);
+/* Pre-populate: make the keys of the integer feature ids [first_id, first_id + count) exist with default
+ * contents, as a Pull of them would (store[key], ftrl.h:56,114-120); ids are hashed on the device as their
+ * decimal strings (load_data_from_disk.cc:151).  A sharded table keeps only the keys of its own range.
+ * Asynchronous on the table's stream. */
+XF_DLL int xf_table_touch_decimal_ids(xf_table* t, uint64_t first_id, uint64_t count);
 /* copy up to max_keys live keys to host; *n_out = number of live keys */
 XF_DLL int xf_table_list_keys(xf_table* t, uint64_t* keys_out, uint64_t max_keys, uint64_t* n_out);
 /* binary checkpoint of the whole shard (keys + full optimizer state) */
@@ -191,6 +196,13 @@ XF_DLL int xf_hash_decimal_ids_device(const uint32_t* d_ids, uint64_t n, uint64_
  * the device, and reports its size.  xf_trainer_step_ingested / _predict_ingested then run the step on a
  * row range [row_start, row_end) of that block (the reference's per-thread slices, lr_worker.cc:190-196). */
 XF_DLL int xf_trainer_ingest_text(xf_trainer* tr, const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz);
+/* The same in two phases, for pipelined callers: _begin enqueues the copy and the parse of the NEXT block on
+ * the trainer's ingest stream (two device-side block buffers) and returns at once; `text` must stay untouched
+ * until _end returns (page-locked memory is copied by DMA, pageable memory is staged first).  _end waits for
+ * that parse only — not for training steps still running on the previous block — and makes the block
+ * current.  One block may be in flight. */
+XF_DLL int xf_trainer_ingest_begin(xf_trainer* tr, const char* text, uint64_t len);
+XF_DLL int xf_trainer_ingest_end(xf_trainer* tr, uint32_t* rows, uint32_t* nnz);
 XF_DLL int xf_trainer_step_ingested(xf_trainer* tr, uint32_t row_start, uint32_t row_end);
 /* copy the ingested block's CSR back to host arrays of rows+1 / nnz / rows elements (any may be NULL) */
 XF_DLL int xf_trainer_ingested_export(xf_trainer* tr, uint32_t* row_ptr_out, uint64_t* keys_out, uint8_t* labels_out);
@@ -226,32 +238,37 @@ typedef struct xf_loader xf_loader;
 /* replaces: xflow::LoadData(path, block_bytes) (load_data_from_disk.h:19-21) */
 XF_DLL int xf_loader_open(xf_loader** out, const char* path, uint64_t block_bytes);
 XF_DLL int xf_loader_close(xf_loader* l);
+/* restart at the first byte (what re-opening the file at the top of every epoch does, lr_worker.cc:184) */
+XF_DLL int xf_loader_rewind(xf_loader* l);
 /* replaces: load_minibatch_hash_data_fread (load_data_from_disk.cc:103-210): parse the next block.
  * *rows = 0 at end of file.  The CSR arrays stay valid until the next call. */
 XF_DLL int xf_loader_next(xf_loader* l, uint32_t* rows, uint32_t* nnz);
 XF_DLL int xf_loader_batch(xf_loader* l, const uint32_t** row_ptr, const uint64_t** keys, const uint8_t** labels);
 /* block formation only (load_data_from_disk.cc:108-124): the next block's raw text, for the device parser
- * (xf_trainer_ingest_text).  *len = 0 at end of file.  The text stays valid until the next call. */
+ * (xf_trainer_ingest_text / _begin).  *len = 0 at end of file.  The loader alternates two (page-locked) text
+ * buffers: a block's text stays valid until the call AFTER the next one.  Tab-less rows ("0\n") count as rows
+ * without features on the device parser; the host parser (xf_loader_next), like the reference, scans on to the
+ * next tab and merges them into the following row. */
 XF_DLL int xf_loader_next_raw(xf_loader* l, const char** text, uint64_t* len);
 
 /* ------------------------------------------------------------------------------------------------
- * 5. Multi-GPU exchange (one process per GPU; NCCL over NVLink)
+ * 5. Multi-GPU exchange (one process per GPU over NVLink / NVSwitch).  A trainer created with a comm of
+ *    N ranks runs the sharded step (csrc/comm.cu): every rank must create its trainer with the same
+ *    max_rows / max_nnz / model and call the step / predict entry points the same number of times, in the
+ *    same order (an empty batch is a valid step).  NCCL serves bootstrap only (exchange of cudaIpc handles);
+ *    inside a step kernels store into the peers' memory directly.
  * ---------------------------------------------------------------------------------------------- */
 #define XF_COMM_ID_BYTES 128
 /* rank 0 creates the id and distributes it out of band (file, MPI, torch.distributed ...) */
 XF_DLL int xf_comm_get_id(uint8_t id[XF_COMM_ID_BYTES]);
 XF_DLL int xf_comm_create(xf_comm** out, const uint8_t id[XF_COMM_ID_BYTES], int rank, int nranks, int device);
+/* the same with the id passed through a file: rank 0 writes it, the others wait for it (launchers that have no
+ * other channel, e.g. the reference's CLI started once per GPU with XFLOW_RANK / XFLOW_WORLD) */
+XF_DLL int xf_comm_create_from_file(xf_comm** out, const char* path, int rank, int nranks, int device);
+/* max over the ranks of one host value (blocking; to agree on the number of collective steps) */
+XF_DLL int xf_comm_allreduce_max(xf_comm* c, uint64_t* inout);
 XF_DLL int xf_comm_destroy(xf_comm* c);
 XF_DLL int xf_comm_barrier(xf_comm* c);
-/* Host-side plan of the sharded step's three exchanges (comm.cu), a pure function exposed for tests:
- * counts[p*S+q] = unique keys of worker p's batch owned by shard q; offsets in keys, bucket stride `cap`.
- * send_* : my bucket q (request / push to owner q, its answers land there); recv_* : source q's segment of my
- * owner-side arrays; own_off[q] : my share inside worker q's arrays; resp_off[q] : my answers inside owner
- * q's response arrays.  All outputs are arrays of S elements. */
-XF_DLL int xf_exchange_plan(const uint32_t* counts, int S, int rank, uint64_t cap, uint64_t* send_off,
-                            uint64_t* send_cnt, uint64_t* recv_off, uint64_t* recv_cnt, uint64_t* own_off,
-                            uint64_t* resp_off);
-
 /* ------------------------------------------------------------------------------------------------
  * 1. Reference C API (src/c_api/c_api.h:26-29), unchanged signatures.
  *    XFCreate builds an LR worker on <train_path>-%05d / <test_path>-%05d (rank from XFLOW_RANK,

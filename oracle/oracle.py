@@ -322,8 +322,10 @@ def read_dump(path):
 
 
 def run_ref(model, opt, train_prefix, test_prefix, epochs, cwd, core=1, block_mb=2, vdim=10,
-            dump=None, preinit_dump=None, no_predict=False, fix_time=None, extra=()):
-    """Run the compiled reference; returns dict(stdout, train_seconds, logloss, auc, pred_path)."""
+            dump=None, preinit_dump=None, no_predict=False, fix_time=None, extra=(), servers=1, warm_epochs=0):
+    """Run the compiled reference; returns dict(stdout, train_seconds, logloss, auc, pred_path).
+    servers / warm_epochs are benchmark-only (ref_harness.cc): key-range server shards in the shim, and
+    extra epochs timed on the warm table (-> warm_seconds)."""
     cmd = [REF_BIN, "--model", model, "--opt", opt, "--train", train_prefix, "--test", test_prefix,
            "--epochs", str(epochs), "--core", str(core), "--block-mb", str(block_mb), "--vdim", str(vdim)]
     if dump:
@@ -334,12 +336,18 @@ def run_ref(model, opt, train_prefix, test_prefix, epochs, cwd, core=1, block_mb
         cmd += ["--no-predict"]
     if fix_time is not None:
         cmd += ["--fix-time", repr(float(fix_time))]
+    if servers > 1:
+        cmd += ["--servers", str(servers)]
+    if warm_epochs > 0:
+        cmd += ["--warm-epochs", str(warm_epochs)]
     cmd += list(extra)
     res = subprocess.run(cmd, cwd=cwd, capture_output=True, text=True, check=True)
     out = {"stdout": res.stdout, "pred_path": os.path.join(cwd, "pred_0_0.txt")}
     for line in res.stdout.splitlines():
         if line.startswith("XFREF train_seconds"):
             out["train_seconds"] = float(line.split()[-1])
+        if line.startswith("XFREF warm_seconds"):
+            out["warm_seconds"] = float(line.split()[-1])
         if line.startswith("logloss:"):
             toks = line.replace("=", " ").split()
             out["logloss"] = float(toks[1])

@@ -73,6 +73,8 @@ double now_s() {
 struct Args {
   std::string model = "lr", opt = "ftrl", train, test, dump, preinit_dump;
   int epochs = 1, core = 1, block_mb = 2, vdim = 10;
+  int servers = 1;      // benchmark only: key-range server shards in the shim (see oracle/shim/ps/ps.h)
+  int warm_epochs = 0;  // benchmark only: after the timed cold run, time this many more epochs on the warm table
   bool no_predict = false;
 };
 
@@ -122,6 +124,8 @@ int main(int argc, char** argv) {
     else if (s == "--dump") a.dump = next();
     else if (s == "--preinit-dump") a.preinit_dump = next();
     else if (s == "--no-predict") a.no_predict = true;
+    else if (s == "--servers") a.servers = atoi(next());
+    else if (s == "--warm-epochs") a.warm_epochs = atoi(next());
     else if (s == "--fix-time") { g_fix_time = true; g_fixed_time = atof(next()); }
     else { fprintf(stderr, "unknown arg %s\n", s.c_str()); return 2; }
   }
@@ -145,6 +149,19 @@ int main(int argc, char** argv) {
   } else {
     server_w->set_request_handle(std::ref(sgd_w));
     server_v->set_request_handle(std::ref(sgd_v));
+  }
+
+  if (a.servers > 1) {
+    if (!a.dump.empty() || !a.preinit_dump.empty()) { fprintf(stderr, "--servers > 1 cannot dump\n"); return 2; }
+    for (int i = 1; i < a.servers; ++i) {
+      if (ftrl) {
+        server_w->add_shard_handle(xflow::FTRL::KVServerFTRLHandle_w());
+        server_v->add_shard_handle(xflow::FTRL::KVServerFTRLHandle_v());
+      } else {
+        server_w->add_shard_handle(xflow::SGD::KVServerSGDHandle_w());
+        server_v->add_shard_handle(xflow::SGD::KVServerSGDHandle_v());
+      }
+    }
   }
 
   std::vector<ps::Key> all_keys;
@@ -182,7 +199,7 @@ int main(int argc, char** argv) {
     fclose(f);
   }
 
-  double t_train = 0.0;
+  double t_train = 0.0, t_warm = 0.0;
   if (fm) {
     xflow::FMWorker* wk = new xflow::FMWorker(a.train.c_str(), a.test.c_str());
     wk->epochs = a.epochs;
@@ -196,6 +213,12 @@ int main(int argc, char** argv) {
       double t0 = now_s();
       wk->batch_training(wk->pool_);
       t_train = now_s() - t0;
+      if (a.warm_epochs > 0) {  // the same shard again, every key already in the store
+        wk->epochs = a.warm_epochs;
+        t0 = now_s();
+        wk->batch_training(wk->pool_);
+        t_warm = now_s() - t0;
+      }
     } else {
       double t0 = now_s();
       wk->train();
@@ -213,6 +236,12 @@ int main(int argc, char** argv) {
       double t0 = now_s();
       wk->batch_training(wk->pool_);
       t_train = now_s() - t0;
+      if (a.warm_epochs > 0) {  // the same shard again, every key already in the store
+        wk->epochs = a.warm_epochs;
+        t0 = now_s();
+        wk->batch_training(wk->pool_);
+        t_warm = now_s() - t0;
+      }
     } else {
       double t0 = now_s();
       wk->train();
@@ -220,6 +249,7 @@ int main(int argc, char** argv) {
     }
   }
   printf("XFREF train_seconds %.6f\n", t_train);
+  if (a.warm_epochs > 0) printf("XFREF warm_seconds %.6f\n", t_warm);
 
   if (!a.dump.empty()) {
     uint64_t n = all_keys.size();

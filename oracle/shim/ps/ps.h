@@ -17,6 +17,15 @@
 // Push/Pull invoke the installed request handle synchronously under one mutex
 // per app id, which reproduces "each KV app's handle runs on one receive
 // thread" (ps-lite/src/customer.cc:49-64).
+//
+// Benchmark-only extension (bench.py --impl reference): a KVServer may carry SEVERAL
+// handle instances ("server shards", add_shard_handle), each with its own mutex and
+// its own store, standing for S ps-lite server processes on the same box.  The worker
+// then slices every request by key range exactly like KVWorker::DefaultSlicer
+// (kv_app.h:405-460) over Postoffice::GetServerKeyRanges (postoffice.cc:134-143) and
+// serves the slices one after another from the calling thread; with core_num worker
+// threads in flight the shards work in parallel.  With one shard (the default, and
+// what every parity fixture uses) nothing changes.
 #ifndef ORACLE_SHIM_PS_PS_H_
 #define ORACLE_SHIM_PS_PS_H_
 
@@ -26,7 +35,9 @@
 #include <cmath>
 #include <cstdio>
 #include <functional>
+#include <algorithm>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -86,23 +97,40 @@ class KVServer {
     std::lock_guard<std::mutex> lk(shim::Registry::Get().mu);
     shim::Registry::Get().servers[app_id] = this;
   }
-  void set_request_handle(const ReqHandle& h) { handle_ = h; }
+  void set_request_handle(const ReqHandle& h) {
+    if (shards_.empty()) shards_.emplace_back(new Shard);
+    shards_[0]->handle = h;
+  }
+  void add_shard_handle(const ReqHandle& h) {
+    shards_.emplace_back(new Shard);
+    shards_.back()->handle = h;
+  }
+  size_t num_shards() const { return shards_.size(); }
+  // the handle answers through here; which shard is being served is thread-local
   void Response(const KVMeta& /*req*/, const KVPairs<Val>& res = KVPairs<Val>()) {
-    if (pending_vals_ != nullptr) *pending_vals_ = res.vals;
+    std::vector<Val>*& pending = Pending();
+    if (pending != nullptr) *pending = res.vals;
   }
   // used by KVWorker below
-  void Serve(const KVMeta& meta, const KVPairs<Val>& req, std::vector<Val>* out) {
-    std::lock_guard<std::mutex> lk(mu_);
-    pending_vals_ = out;
-    handle_(meta, req, this);
-    pending_vals_ = nullptr;
+  void Serve(size_t shard, const KVMeta& meta, const KVPairs<Val>& req, std::vector<Val>* out) {
+    Shard& sh = *shards_[shard];
+    std::lock_guard<std::mutex> lk(sh.mu);
+    Pending() = out;
+    sh.handle(meta, req, this);
+    Pending() = nullptr;
   }
 
  private:
+  struct Shard {
+    ReqHandle handle;
+    std::mutex mu;
+  };
+  static std::vector<Val>*& Pending() {
+    static thread_local std::vector<Val>* p = nullptr;
+    return p;
+  }
   int app_id_;
-  ReqHandle handle_;
-  std::mutex mu_;
-  std::vector<Val>* pending_vals_ = nullptr;
+  std::vector<std::unique_ptr<Shard>> shards_;
 };
 
 template <typename Val>
@@ -116,7 +144,7 @@ class KVWorker {
     req.vals = vals;
     req.lens = lens;
     KVMeta m{cmd, true, 0, ts_};
-    server()->Serve(m, req, nullptr);
+    Dispatch(m, req, nullptr);
     return ts_++;
   }
   int Pull(const std::vector<Key>& keys, std::vector<Val>* vals,
@@ -125,12 +153,38 @@ class KVWorker {
     KVPairs<Val> req;
     req.keys = keys;
     KVMeta m{cmd, false, 0, ts_};
-    server()->Serve(m, req, vals);
+    Dispatch(m, req, vals);
     return ts_++;
   }
   void Wait(int /*timestamp*/) {}
 
  private:
+  void Dispatch(const KVMeta& m, const KVPairs<Val>& req, std::vector<Val>* out) {
+    KVServer<Val>* sv = server();
+    const size_t S = sv->num_shards();
+    if (S <= 1) {
+      sv->Serve(0, m, req, out);
+      return;
+    }
+    // DefaultSlicer: keys are sorted; server i owns [width*i, width*(i+1)), width = floor((2^64-1)/S)
+    const Key width = (Key)0xFFFFFFFFFFFFFFFFull / (Key)S;
+    const size_t n = req.keys.size();
+    const size_t dim = (n && !req.vals.empty()) ? req.vals.size() / n : 0;
+    if (out) out->clear();
+    size_t beg = 0;
+    for (size_t i = 0; i < S && beg < n; ++i) {
+      size_t end = n;
+      if (i + 1 < S) end = std::lower_bound(req.keys.begin() + beg, req.keys.end(), width * (Key)(i + 1)) - req.keys.begin();
+      if (end == beg) continue;
+      KVPairs<Val> part;
+      part.keys.assign(req.keys.begin() + beg, req.keys.begin() + end);
+      if (dim) part.vals.assign(req.vals.begin() + beg * dim, req.vals.begin() + end * dim);
+      std::vector<Val> got;
+      sv->Serve(i, m, part, out ? &got : nullptr);
+      if (out) out->insert(out->end(), got.begin(), got.end());
+      beg = end;
+    }
+  }
   KVServer<Val>* server() {
     auto& r = shim::Registry::Get();
     std::lock_guard<std::mutex> lk(r.mu);

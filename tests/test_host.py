@@ -218,44 +218,6 @@ def test_raw_blocks_are_the_parsed_blocks(block_bytes):
     assert b"".join(r.rstrip(b"\n") for r in raw).replace(b"\n", b"") == whole.replace(b"\n", b"")
 
 
-@pytest.mark.parametrize("S", [1, 2, 3, 8])
-def test_exchange_plan_moves_every_key_to_its_owner_and_back(S):
-    """xf_exchange_plan (the host logic of comm.cu's three exchanges): simulate every rank's buffers in numpy
-    and carry out the peer reads exactly as xf_mg_step issues them."""
-    rng = np.random.default_rng(S)
-    cap = 64
-    counts = rng.integers(0, cap + 1, (S, S)).astype(np.uint32)
-    counts[rng.integers(0, S), rng.integers(0, S)] = 0          # an empty bucket somewhere
-    plans = [api.exchange_plan(counts, r, cap) for r in range(S)]
-    # worker p's bucket-major request array: element i of bucket q is tagged (p, q, i)
-    tag = lambda p, q, i: (p << 40) | (q << 20) | i
-    req = [np.full(S * cap, -1, np.int64) for _ in range(S)]
-    for p in range(S):
-        for q in range(S):
-            req[p][q * cap:q * cap + counts[p, q]] = [tag(p, q, i) for i in range(counts[p, q])]
-    # exchange 1 (and 3): owner r reads its share out of every worker's array
-    recv = []
-    for r, pl in enumerate(plans):
-        buf = np.full(int(counts[:, r].sum()), -2, np.int64)
-        for q in range(S):
-            n = int(pl["recv_cnt"][q])
-            assert n == counts[q, r]
-            buf[int(pl["recv_off"][q]):int(pl["recv_off"][q]) + n] = req[q][int(pl["own_off"][q]):int(pl["own_off"][q]) + n]
-        want = [tag(q, r, i) for q in range(S) for i in range(counts[q, r])]   # grouped by source, in rank order
-        assert buf.tolist() == want
-        recv.append(buf)
-    # exchange 2: the owner answers in place (answer = request + 1); worker r reads its answers back
-    resp = [b + 1 for b in recv]
-    for r, pl in enumerate(plans):
-        got = np.full(S * cap, -3, np.int64)
-        for q in range(S):
-            n = int(pl["send_cnt"][q])
-            assert n == counts[r, q] and pl["send_off"][q] == q * cap
-            got[q * cap:q * cap + n] = resp[q][int(pl["resp_off"][q]):int(pl["resp_off"][q]) + n]
-        live = req[r] >= 0
-        assert np.array_equal(got[live], req[r][live] + 1) and (got[~live] == -3).all()
-
-
 def test_loader_fuzz_against_python_parser(tmp_path):
     """Random well-formed shards (random labels incl. floats, 0..6 tokens per row, fids of random bytes and
     lengths, CRLF or LF, with / without final newline) cut at random block sizes: the rows, labels and

@@ -54,6 +54,7 @@ SIGNATURES = {
     "xf_table_row_bytes": (_i, [_vp, _vp]),
     "xf_table_reserve": (_i, [_vp, _u64]),
     "xf_table_list_keys": (_i, [_vp, _vp, _u64, _vp]),
+    "xf_table_touch_decimal_ids": (_i, [_vp, _u64, _u64]),
     "xf_table_save": (_i, [_vp, C.c_char_p]),
     "xf_table_load": (_i, [_vp, C.c_char_p]),
     "xf_table_set_stream": (_i, [_vp, _vp]),
@@ -76,6 +77,8 @@ SIGNATURES = {
     "xf_auc_logloss_exact": (_i, [_vp, _vp, _u64, _vp]),
     "xf_table_dump_text": (_i, [_vp, C.c_char_p, _i, _vp]),
     "xf_trainer_ingest_text": (_i, [_vp, _vp, _u64, _vp, _vp]),
+    "xf_trainer_ingest_begin": (_i, [_vp, _vp, _u64]),
+    "xf_trainer_ingest_end": (_i, [_vp, _vp, _vp]),
     "xf_trainer_step_ingested": (_i, [_vp, _u32, _u32]),
     "xf_trainer_ingested_export": (_i, [_vp, _vp, _vp, _vp]),
     "xf_trainer_predict_ingested": (_i, [_vp, _u32, _u32, _vp, _vp]),
@@ -89,13 +92,15 @@ SIGNATURES = {
     "xf_hash_decimal_ids": (_i, [_vp, _u64, _vp]),
     "xf_loader_open": (_i, [_vp, C.c_char_p, _u64]),
     "xf_loader_close": (_i, [_vp]),
+    "xf_loader_rewind": (_i, [_vp]),
     "xf_loader_next": (_i, [_vp, _vp, _vp]),
     "xf_loader_batch": (_i, [_vp, _vp, _vp, _vp]),
     "xf_comm_get_id": (_i, [_vp]),
     "xf_comm_create": (_i, [_vp, _vp, _i, _i, _i]),
+    "xf_comm_create_from_file": (_i, [_vp, C.c_char_p, _i, _i, _i]),
+    "xf_comm_allreduce_max": (_i, [_vp, _vp]),
     "xf_comm_destroy": (_i, [_vp]),
     "xf_comm_barrier": (_i, [_vp]),
-    "xf_exchange_plan": (_i, [_vp, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "XFCreate": (_i, [_vp, C.c_char_p, C.c_char_p]),
     "XFStartTrain": (_i, [_vp]),
     "XFCreateEx": (_i, [_vp, C.c_char_p, C.c_char_p, _i, _i, _i, _i]),
@@ -280,6 +285,9 @@ class Table:
     def reserve(self, n_keys):
         _check(lib().xf_table_reserve(self.h, int(n_keys)))
 
+    def touch_decimal_ids(self, first_id, count):
+        _check(lib().xf_table_touch_decimal_ids(self.h, int(first_id), int(count)))
+
     def list_keys(self):
         n = self.size()
         keys = np.empty(max(n, 1), np.uint64)
@@ -303,16 +311,6 @@ class Table:
 
     def sync(self):
         _check(lib().xf_table_sync(self.h))
-
-
-def exchange_plan(counts, rank, cap):
-    """comm.cu's exchange plan for `rank`: dict of S-element offset / count arrays (see xflow_b200.h)."""
-    counts = np.ascontiguousarray(counts, np.uint32)
-    S = counts.shape[0]
-    names = ("send_off", "send_cnt", "recv_off", "recv_cnt", "own_off", "resp_off")
-    out = {n: np.zeros(S, np.uint64) for n in names}
-    _check(lib().xf_exchange_plan(_p(counts), S, rank, cap, *[_p(out[n]) for n in names]))
-    return out
 
 
 class Comm:

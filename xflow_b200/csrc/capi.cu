@@ -137,18 +137,16 @@ int xf_table::grow(uint64_t new_capacity) {
   return XF_OK;
 }
 
+// Lazy tables number their batches (sharded: every (step, source) pair) with `seq`; rows_by_seq[seq] is the
+// divisor of that batch's pending optimizer steps.  The array is a fixed ring: when the numbers run out,
+// one sweep folds every pending step into its row (xf_k_flush_pending, stream-ordered, no host sync) and
+// the numbering restarts at 1 — no reallocation, no 32-bit wrap into XF_TAG_LOCKED.
 int xf_table::next_seq() {
-  if ((size_t)seq + 2 >= rows_cap) {
-    const size_t ncap = rows_cap * 2;
-    uint32_t* nbuf = nullptr;
-    XF_CUDA_TRY(cudaMalloc(&nbuf, ncap * sizeof(uint32_t)));
-    XF_CUDA_TRY(cudaMemsetAsync(nbuf, 0, ncap * sizeof(uint32_t), stream));
-    XF_CUDA_TRY(cudaMemcpyAsync(nbuf, d_rows_by_seq, rows_cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-    XF_CUDA_TRY(cudaStreamSynchronize(stream));
-    XF_CUDA_TRY(cudaFree(d_rows_by_seq));
-    d_rows_by_seq = nbuf;
-    rows_cap = ncap;
-    view.rows_by_seq = nbuf;
+  if ((size_t)seq + 1 >= rows_cap) {
+    xf_launch_flush_pending(view, stream);
+    ++launches;
+    XF_CUDA_TRY(cudaGetLastError());
+    seq = 0;
   }
   ++seq;
   return XF_OK;
@@ -233,7 +231,9 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
   v.lazy = (v.K == 0 && !(eager && *eager == '1')) ? 1 : 0;
   v.rows_by_seq = nullptr;
   if (v.lazy) {
-    t->rows_cap = 1u << 16;
+    // XFLOW_SEQ_RING: ring size override (tests exercise the flush with a tiny ring)
+    const char* ring = getenv("XFLOW_SEQ_RING");
+    t->rows_cap = (ring && atoi(ring) >= 4) ? (size_t)atoi(ring) : ((size_t)1 << 20);
     XF_CUDA_TRY(cudaMalloc(&t->d_rows_by_seq, t->rows_cap * sizeof(uint32_t)));
     XF_CUDA_TRY(cudaMemsetAsync(t->d_rows_by_seq, 0, t->rows_cap * sizeof(uint32_t), t->stream));
     v.rows_by_seq = t->d_rows_by_seq;
@@ -579,7 +579,11 @@ XF_DLL int xf_trainer_create(xf_trainer** out, xf_table* table, xf_comm* comm, c
   tr->comm = comm;
   tr->cfg = *cfg;
   XF_CUDA_TRY(cudaStreamCreateWithFlags(&tr->copy_stream, cudaStreamNonBlocking));
+  XF_CUDA_TRY(cudaStreamCreateWithFlags(&tr->ing_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
+    XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->ing[i].parsed, cudaEventDisableTiming));
+    XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->ing[i].consumed, cudaEventDisableTiming));
+    XF_CUDA_TRY(cudaHostAlloc(&tr->ing[i].h_totals, 16, cudaHostAllocDefault));
     XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->buf[i].copied, cudaEventDisableTiming));
     XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->buf[i].consumed, cudaEventDisableTiming));
     XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->buf[i].staged, cudaEventDisableTiming));
@@ -622,8 +626,16 @@ XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
     cudaEventDestroy(b.copied); cudaEventDestroy(b.consumed); cudaEventDestroy(b.staged);
   }
   tr->touched.release(); tr->loss.release(); tr->pctr.release();
-  tr->ing_text.release(); tr->ing_scratch.release(); tr->ing_row_ptr.release(); tr->ing_keys.release();
-  tr->ing_labels.release(); tr->ing_totals.release(); tr->ing_stage.release();
+  cudaStreamSynchronize(tr->ing_stream);
+  for (int i = 0; i < 2; ++i) {
+    xf_trainer::IngestSet& g = tr->ing[i];
+    g.text.release(); g.row_ptr.release(); g.keys.release(); g.labels.release(); g.totals.release(); g.stage.release();
+    if (g.h_totals) cudaFreeHost(g.h_totals);
+    if (g.parsed) cudaEventDestroy(g.parsed);
+    if (g.consumed) cudaEventDestroy(g.consumed);
+  }
+  tr->ing_scratch.release();
+  cudaStreamDestroy(tr->ing_stream);
   cudaFree(tr->d_unique_total); cudaFree(tr->d_abs_loss);
   cudaFreeHost(tr->h_abs_loss);
   cudaStreamDestroy(tr->copy_stream);
@@ -646,7 +658,7 @@ static int xf_check_batch(xf_trainer* tr, uint32_t rows, uint32_t nnz) {
 static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys,
                                const uint8_t* d_labels, uint32_t rows, uint32_t nnz, int mode, float* d_abs) {
   xf_table* t = tr->table;
-  if (rows == 0) return XF_OK;
+  if (rows == 0 && !tr->mg) return XF_OK;     // sharded: an empty batch still takes part in the exchange
   if (!tr->mg) XF_TRY(t->ensure_room(nnz));  // the sharded path sizes the shard from what it receives
   cudaStream_t st = t->stream;
   const bool prof = tr->profile && mode == 0;
@@ -756,7 +768,7 @@ XF_DLL int xf_trainer_step_host(xf_trainer* tr, const uint32_t* row_ptr, const u
                                 const uint8_t* labels, uint32_t rows, uint32_t nnz, float* mean_abs_loss) {
   if (!tr || !row_ptr || (!keys && nnz) || !labels) return XF_ERR_ARG;
   XF_TRY(xf_check_batch(tr, rows, nnz));
-  if (rows == 0) { if (mean_abs_loss) *mean_abs_loss = 0.f; return XF_OK; }
+  if (rows == 0 && !tr->mg) { if (mean_abs_loss) *mean_abs_loss = 0.f; return XF_OK; }
   XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
   const int slot = (int)(tr->step_index & 1);
   XfBatchBuf& b = tr->buf[slot];
@@ -775,7 +787,7 @@ XF_DLL int xf_trainer_step_host(xf_trainer* tr, const uint32_t* row_ptr, const u
     XF_CUDA_TRY(cudaMemcpyAsync(tr->h_abs_loss + slot, tr->d_abs_loss + slot, sizeof(float),
                                 cudaMemcpyDeviceToHost, st));
     XF_CUDA_TRY(cudaStreamSynchronize(st));
-    *mean_abs_loss = tr->h_abs_loss[slot] / (float)rows;
+    *mean_abs_loss = rows ? tr->h_abs_loss[slot] / (float)rows : 0.f;
   }
   return XF_OK;
 }
@@ -784,14 +796,14 @@ XF_DLL int xf_trainer_predict_host(xf_trainer* tr, const uint32_t* row_ptr, cons
                                    uint32_t nnz, float* pctr_out) {
   if (!tr || !row_ptr || (!keys && nnz) || !pctr_out) return XF_ERR_ARG;
   XF_TRY(xf_check_batch(tr, rows, nnz));
-  if (rows == 0) return XF_OK;
+  if (rows == 0 && !tr->mg) return XF_OK;
   XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
   const int slot = (int)(tr->step_index & 1);
   XfBatchBuf& b = tr->buf[slot];
   ++tr->step_index;
   XF_TRY(xf_upload_batch(tr, b, row_ptr, keys, nullptr, rows, nnz));
   cudaStream_t st = tr->table->stream;
-  XF_TRY(b.labels.ensure(rows));  // unused by mode 1 but must be a valid pointer
+  XF_TRY(b.labels.ensure((size_t)rows + 1));  // unused by mode 1 but must be a valid pointer
   XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows,
                              nnz, 1, nullptr));
   XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
@@ -832,7 +844,9 @@ XF_DLL int xf_trainer_stats(xf_trainer* tr, uint64_t* steps, uint64_t* rows, uin
     unsigned long long u = 0;
     XF_CUDA_TRY(cudaMemcpyAsync(&u, tr->d_unique_total, sizeof(u), cudaMemcpyDeviceToHost, tr->table->stream));
     XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
-    *unique_keys = u + tr->host_unique;
+    unsigned long long remote = 0;  // sharded: counted by the owners of this rank's keys
+    if (tr->mg) XF_TRY(xf_mg_unique(tr, &remote));
+    *unique_keys = u + remote;
   }
   return XF_OK;
 }
@@ -860,7 +874,7 @@ XF_DLL int xf_trainer_step_host_async(xf_trainer* tr, const uint32_t* row_ptr, c
                                       float* pinned_abs_loss_sum) {
   if (!tr || !row_ptr || (!keys && nnz) || !labels) return XF_ERR_ARG;
   XF_TRY(xf_check_batch(tr, rows, nnz));
-  if (rows == 0) return XF_OK;
+  if (rows == 0 && !tr->mg) return XF_OK;
   if (!xf_is_pinned(row_ptr) || !xf_is_pinned(keys) || !xf_is_pinned(labels) ||
       (pinned_abs_loss_sum && !xf_is_pinned(pinned_abs_loss_sum))) {
     xf_set_error("xf_trainer_step_host_async needs page-locked host buffers");
@@ -890,7 +904,7 @@ XF_DLL int xf_trainer_step_host_ids_async(xf_trainer* tr, const uint32_t* row_pt
                                           float* pinned_abs_loss_sum) {
   if (!tr || !row_ptr || (!ids && nnz) || !labels) return XF_ERR_ARG;
   XF_TRY(xf_check_batch(tr, rows, nnz));
-  if (rows == 0) return XF_OK;
+  if (rows == 0 && !tr->mg) return XF_OK;
   if (!xf_is_pinned(row_ptr) || !xf_is_pinned(ids) || !xf_is_pinned(labels) ||
       (pinned_abs_loss_sum && !xf_is_pinned(pinned_abs_loss_sum))) {
     xf_set_error("xf_trainer_step_host_ids_async needs page-locked host buffers");
@@ -928,48 +942,78 @@ XF_DLL int xf_trainer_step_host_ids_async(xf_trainer* tr, const uint32_t* row_pt
   return XF_OK;
 }
 
-XF_DLL int xf_trainer_ingest_text(xf_trainer* tr, const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz) {
-  if (!tr || (!text && len) || !rows || !nnz) return XF_ERR_ARG;
+// Two-phase ingest.  _begin copies the block to the device and parses it on the trainer's ingest stream
+// into the set that is NOT being trained on, and returns at once; _end waits for that parse only, makes
+// the set current and reports its size.  A caller that reads block i+1 from disk between _begin(i+1)... see
+// WorkerBase::batch_training (worker.cc): read, H2D, parse of block i+1 overlap the step of block i.
+XF_DLL int xf_trainer_ingest_begin(xf_trainer* tr, const char* text, uint64_t len) {
+  if (!tr || (!text && len)) return XF_ERR_ARG;
+  if (tr->ing_pending) { xf_set_error("ingest: xf_trainer_ingest_begin called twice without xf_trainer_ingest_end"); return XF_ERR_STATE; }
   if (len >= 0xFFFFFFF0ull) { xf_set_error("ingest: a block must be smaller than 4 GiB (u32 token offsets)"); return XF_ERR_ARG; }
   XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
-  cudaStream_t st = tr->table->stream;
-  // upper bounds for a block of `len` bytes: shortest row "0\ta:b:c\n" = 8 bytes, shortest extra token 6 bytes
-  const uint32_t max_rows = (uint32_t)std::min<uint64_t>(len / 2 + 2, tr->cfg.max_rows);
-  const uint32_t max_tok = (uint32_t)std::min<uint64_t>(len / 4 + 2, tr->cfg.max_nnz);
-  XF_TRY(tr->ing_text.ensure(len + 16));
-  XF_TRY(tr->ing_row_ptr.ensure(((size_t)max_rows + 2) * 4));
-  XF_TRY(tr->ing_keys.ensure(((size_t)max_tok + 1) * 8));
-  XF_TRY(tr->ing_labels.ensure((size_t)max_rows + 1));
-  XF_TRY(tr->ing_totals.ensure(16));
+  xf_trainer::IngestSet& g = tr->ing[tr->ing_cur ^ 1];
+  cudaStream_t is = tr->ing_stream;
+  // the steps that read this set (two blocks ago) must have finished before it is overwritten
+  XF_CUDA_TRY(cudaStreamWaitEvent(is, g.consumed, 0));
+  // upper bounds for a block of `len` bytes: shortest row "0\n" = 2 bytes, shortest token "a:b:c " ~ 4 bytes
+  g.max_rows = (uint32_t)std::min<uint64_t>(len / 2 + 2, tr->cfg.max_rows);
+  g.max_tok = (uint32_t)std::min<uint64_t>(len / 4 + 2, tr->cfg.max_nnz);
+  XF_TRY(g.text.ensure(len + 16));
+  XF_TRY(g.row_ptr.ensure(((size_t)g.max_rows + 2) * 4));
+  XF_TRY(g.keys.ensure(((size_t)g.max_tok + 1) * 8));
+  XF_TRY(g.labels.ensure((size_t)g.max_rows + 1));
+  XF_TRY(g.totals.ensure(16));
   const void* src = text;
   if (len && !xf_is_pinned(text)) {
-    XF_TRY(tr->ing_stage.ensure(len));
-    memcpy(tr->ing_stage.p, text, len);
-    src = tr->ing_stage.p;
+    XF_CUDA_TRY(cudaEventSynchronize(g.parsed));  // the stage may still be the source of this set's previous H2D
+    XF_TRY(g.stage.ensure(len));
+    memcpy(g.stage.p, text, len);
+    src = g.stage.p;
   }
-  if (len) XF_CUDA_TRY(cudaMemcpyAsync(tr->ing_text.p, src, len, cudaMemcpyHostToDevice, st));
+  if (len) XF_CUDA_TRY(cudaMemcpyAsync(g.text.p, src, len, cudaMemcpyHostToDevice, is));
   // totals = {rows, tokens, parse error}; the parser's error word is its own, not the table's sticky one
-  XF_CUDA_TRY(cudaMemsetAsync(tr->ing_totals.p, 0, 16, st));
-  XF_TRY(xf_launch_parse(tr->ing_text.as<char>(), len, tr->ing_scratch, tr->ing_row_ptr.as<uint32_t>(),
-                         tr->ing_keys.as<uint64_t>(), tr->ing_labels.as<uint8_t>(), max_rows, max_tok,
-                         tr->ing_totals.as<uint32_t>(), tr->ing_totals.as<int>() + 2, st));
+  XF_CUDA_TRY(cudaMemsetAsync(g.totals.p, 0, 16, is));
+  XF_TRY(xf_launch_parse(g.text.as<char>(), len, tr->ing_scratch, g.row_ptr.as<uint32_t>(), g.keys.as<uint64_t>(),
+                         g.labels.as<uint8_t>(), g.max_rows, g.max_tok, g.totals.as<uint32_t>(), g.totals.as<int>() + 2, is));
   tr->launches += 5;
-  uint32_t tot[3] = {0, 0, 0};
-  XF_CUDA_TRY(cudaMemcpyAsync(tot, tr->ing_totals.p, 12, cudaMemcpyDeviceToHost, st));
-  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  XF_CUDA_TRY(cudaMemcpyAsync(g.h_totals, g.totals.p, 12, cudaMemcpyDeviceToHost, is));
+  XF_CUDA_TRY(cudaEventRecord(g.parsed, is));
+  tr->ing_pending = true;
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_ingest_end(xf_trainer* tr, uint32_t* rows, uint32_t* nnz) {
+  if (!tr || !rows || !nnz) return XF_ERR_ARG;
+  if (!tr->ing_pending) { xf_set_error("ingest: xf_trainer_ingest_end without xf_trainer_ingest_begin"); return XF_ERR_STATE; }
+  xf_trainer::IngestSet& g = tr->ing[tr->ing_cur ^ 1];
+  tr->ing_pending = false;
+  XF_CUDA_TRY(cudaEventSynchronize(g.parsed));
+  const uint32_t* tot = g.h_totals;
   const int e = (int)tot[2];
-  tr->ing_rows = tr->ing_nnz = 0;
+  g.rows = g.nnz = 0;
   if (e == 4) { xf_set_error("ingest: token without three ':'-separated fields"); return XF_ERR_IO; }
-  if (e == 3 || tot[0] > max_rows || tot[1] > max_tok) {
+  if (e == 3 || tot[0] > g.max_rows || tot[1] > g.max_tok) {
     xf_set_error("ingest: block (%u rows, %u tokens) exceeds trainer limits (%u, %u)", tot[0], tot[1],
                  tr->cfg.max_rows, tr->cfg.max_nnz);
     return XF_ERR_ARG;
   }
-  tr->ing_rows = tot[0];
-  tr->ing_nnz = tot[1];
-  *rows = tot[0];
-  *nnz = tot[1];
+  g.rows = tot[0];
+  g.nnz = tot[1];
+  tr->ing_cur ^= 1;
+  tr->ing_rows = g.rows;
+  tr->ing_nnz = g.nnz;
+  // everything the table stream does with this set comes after its parse
+  XF_CUDA_TRY(cudaStreamWaitEvent(tr->table->stream, g.parsed, 0));
+  *rows = g.rows;
+  *nnz = g.nnz;
   return XF_OK;
+}
+
+XF_DLL int xf_trainer_ingest_text(xf_trainer* tr, const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz) {
+  if (!tr || (!text && len) || !rows || !nnz) return XF_ERR_ARG;
+  tr->ing_rows = tr->ing_nnz = 0;
+  XF_TRY(xf_trainer_ingest_begin(tr, text, len));
+  return xf_trainer_ingest_end(tr, rows, nnz);
 }
 
 static int xf_ingested_range(xf_trainer* tr, uint32_t row_start, uint32_t row_end) {
@@ -984,15 +1028,17 @@ static int xf_ingested_range(xf_trainer* tr, uint32_t row_start, uint32_t row_en
 
 XF_DLL int xf_trainer_step_ingested(xf_trainer* tr, uint32_t row_start, uint32_t row_end) {
   XF_TRY(xf_ingested_range(tr, row_start, row_end));
-  if (row_end == row_start) return XF_OK;
+  if (row_end == row_start && !tr->mg) return XF_OK;
   XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  xf_trainer::IngestSet& g = tr->ing[tr->ing_cur];
   const uint32_t rows = row_end - row_start;
   // row_ptr holds absolute token offsets, so a slice is just a shifted row_ptr / labels pointer; the
   // per-token scratch (FM: touched[]) is indexed by absolute position and must not keep stale slices
-  if (!tr->table->view.lazy)
+  if (!tr->table->view.lazy && !tr->mg)
     XF_CUDA_TRY(cudaMemsetAsync(tr->touched.p, 0xFF, (size_t)tr->ing_nnz * 4, tr->table->stream));
-  XF_TRY(xf_step_device_impl(tr, tr->ing_row_ptr.as<uint32_t>() + row_start, tr->ing_keys.as<uint64_t>(),
-                             tr->ing_labels.as<uint8_t>() + row_start, rows, tr->ing_nnz, 0, nullptr));
+  XF_TRY(xf_step_device_impl(tr, g.row_ptr.as<uint32_t>() + row_start, g.keys.as<uint64_t>(),
+                             g.labels.as<uint8_t>() + row_start, rows, tr->ing_nnz, 0, nullptr));
+  XF_CUDA_TRY(cudaEventRecord(g.consumed, tr->table->stream));
   ++tr->n_steps;
   tr->n_rows += rows;
   tr->last_rows = rows;
@@ -1003,30 +1049,41 @@ XF_DLL int xf_trainer_ingested_export(xf_trainer* tr, uint32_t* row_ptr_out, uin
   if (!tr) return XF_ERR_ARG;
   XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
   XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
+  xf_trainer::IngestSet& g = tr->ing[tr->ing_cur];
   if (row_ptr_out)
-    XF_CUDA_TRY(cudaMemcpy(row_ptr_out, tr->ing_row_ptr.p, ((size_t)tr->ing_rows + 1) * 4, cudaMemcpyDeviceToHost));
+    XF_CUDA_TRY(cudaMemcpy(row_ptr_out, g.row_ptr.p, ((size_t)tr->ing_rows + 1) * 4, cudaMemcpyDeviceToHost));
   if (keys_out && tr->ing_nnz)
-    XF_CUDA_TRY(cudaMemcpy(keys_out, tr->ing_keys.p, (size_t)tr->ing_nnz * 8, cudaMemcpyDeviceToHost));
+    XF_CUDA_TRY(cudaMemcpy(keys_out, g.keys.p, (size_t)tr->ing_nnz * 8, cudaMemcpyDeviceToHost));
   if (labels_out && tr->ing_rows)
-    XF_CUDA_TRY(cudaMemcpy(labels_out, tr->ing_labels.p, (size_t)tr->ing_rows, cudaMemcpyDeviceToHost));
+    XF_CUDA_TRY(cudaMemcpy(labels_out, g.labels.p, (size_t)tr->ing_rows, cudaMemcpyDeviceToHost));
   return XF_OK;
+}
+
+// Forward pass over a row range of the current block.  Asynchronous when pinned result buffers are given
+// (xf_trainer_predict_ingested_async): the caller reads them after xf_trainer_sync.
+static int xf_predict_ingested_impl(xf_trainer* tr, uint32_t row_start, uint32_t row_end, float* pctr_out,
+                                    uint8_t* labels_out, bool sync) {
+  XF_TRY(xf_ingested_range(tr, row_start, row_end));
+  if (row_end == row_start && !tr->mg) return XF_OK;
+  if (!pctr_out) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  xf_trainer::IngestSet& g = tr->ing[tr->ing_cur];
+  const uint32_t rows = row_end - row_start;
+  cudaStream_t st = tr->table->stream;
+  XF_TRY(xf_step_device_impl(tr, g.row_ptr.as<uint32_t>() + row_start, g.keys.as<uint64_t>(),
+                             g.labels.as<uint8_t>() + row_start, rows, tr->ing_nnz, 1, nullptr));
+  if (rows) XF_CUDA_TRY(cudaMemcpyAsync(pctr_out, tr->pctr.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+  if (labels_out && rows)
+    XF_CUDA_TRY(cudaMemcpyAsync(labels_out, g.labels.as<uint8_t>() + row_start, rows, cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaEventRecord(g.consumed, st));
+  if (!sync) return XF_OK;
+  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  return tr->table->check_error();
 }
 
 XF_DLL int xf_trainer_predict_ingested(xf_trainer* tr, uint32_t row_start, uint32_t row_end, float* pctr_out,
                                        uint8_t* labels_out) {
-  XF_TRY(xf_ingested_range(tr, row_start, row_end));
-  if (row_end == row_start) return XF_OK;
-  if (!pctr_out) return XF_ERR_ARG;
-  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
-  const uint32_t rows = row_end - row_start;
-  cudaStream_t st = tr->table->stream;
-  XF_TRY(xf_step_device_impl(tr, tr->ing_row_ptr.as<uint32_t>() + row_start, tr->ing_keys.as<uint64_t>(),
-                             tr->ing_labels.as<uint8_t>() + row_start, rows, tr->ing_nnz, 1, nullptr));
-  XF_CUDA_TRY(cudaMemcpyAsync(pctr_out, tr->pctr.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
-  if (labels_out)
-    XF_CUDA_TRY(cudaMemcpyAsync(labels_out, tr->ing_labels.as<uint8_t>() + row_start, rows, cudaMemcpyDeviceToHost, st));
-  XF_CUDA_TRY(cudaStreamSynchronize(st));
-  return tr->table->check_error();
+  return xf_predict_ingested_impl(tr, row_start, row_end, pctr_out, labels_out, true);
 }
 
 XF_DLL int xf_trainer_set_profile(xf_trainer* tr, int on) {

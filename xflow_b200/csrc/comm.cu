@@ -1,33 +1,41 @@
 // C ABI layer 5: the multi-GPU exchange that replaces ps-lite's KVWorker slicing + ZeroMQ Van
-// (ps-lite/include/ps/kv_app.h:405-460, ps-lite/src/zmq_van.h).  One process per GPU; NCCL over
-// NVLink / NVSwitch.  The communicator id is created by rank 0 and distributed out of band by the
-// launcher (bench.py uses torch.distributed for that and nothing else).
+// (ps-lite/include/ps/kv_app.h:405-460, ps-lite/src/zmq_van.h).  One process per GPU over NVLink /
+// NVSwitch.  NCCL is used for bootstrap only (exchange of the cudaIpc handles, barriers at creation and
+// destruction); the communicator id is created by rank 0 and distributed out of band by the launcher.
 //
-// Every rank is at once a WORKER (its own CSR batch) and the SERVER of one key range
-// (shard = min(key / floor((2^64-1)/S), S-1), postoffice.cc:134-143).  One step =
+// A step never calls NCCL, never synchronises with the host and never moves a count through the host:
+// kernels store into the peers' memory (mg.cuh: one IPC-mapped slab per rank) and order themselves with
+// step counters.  Every rank is at once a WORKER (its own CSR batch) and the OWNER of one key range.
+// Streams of rank r at step t (parity p = t & 1):
 //
-//   worker  dedup the batch's keys into the per-batch work set (workset.cuh): every unique key gets a
-//           number u inside its owner's bucket                            [xf_k_ws_dedup]
-//   all     exchange bucket sizes (ncclAllGather), then keys              [all-to-all #1 = the Pull request]
-//   owner   probe/insert the received keys in its shard, gather w (,v)    [xf_k_probe, xf_k_gather_v]
-//   all     values back, straight into the work set's compact arrays      [all-to-all #2 = the Pull response]
-//   worker  the fused step against the work set (same arithmetic as the single-GPU kernel: forward,
-//           residual, per-key gradient accumulation), then g / rows       [xf_k_step_ws, xf_k_ws_grads]
-//   all     gradients to the owners                                       [all-to-all #3 = the Push]
-//   owner   one FTRL/SGD step per (source rank, key), source ranks applied in rank order — one legal
-//           schedule of the reference's asynchronous multi-worker run (every worker pulled before any
-//           push of the round), reproducible by the oracle                [xf_k_update<.,false> x S]
+//   stream 2 (runs one step ahead)            table stream
+//   --------------------------------          ------------------------------------------------------------
+//   wait  DONE >= t-2 from all owners
+//   xf_k_route  batch t -> owners' in_keys[p]  wait  KEYS >= t from all sources   (+ ROWV >= t-1: vals[] free)
+//   signal KEYS = t (+ bucket sizes, rows)     xf_k_pull_tokens  -> sources' vals[]        (Pull handler)
+//                                              signal VALS = t
+//                                              wait  VALS >= t from all owners
+//                                              xf_k_rows (+ broadcast of the per-row residuals)
+//                                              signal ROWV = t
+//                                              wait  ROWV >= t from all sources
+//                                              for s in 0..S-1:  push kernel(s) of source s  (Push handler,
+//                                                   one optimizer step per (source, key), rank order)
+//                                              signal DONE = t
 //
-// The three all-to-alls are reads from peer memory (cudaIpc-mapped buffers + DMA copies behind a 4-byte
-// NCCL all-reduce, see xf_mg_setup_p2p / xf_mg_pull); grouped ncclSend/ncclRecv on the table's stream is
-// the fallback (XFLOW_P2P=0 or no IPC).  NVSwitch gives every pair the same bandwidth, so a flat
-// all-to-all is the right schedule; at S = 1 none of this runs.
+// Semantics = one legal schedule of the reference's asynchronous run: every worker pulls before any push
+// of the round, pushes land in rank order (tests/test_gpu_multi.py against the oracle's lock-step run).
+// Buffer reuse needs no further signalling: in_keys/in_rows are double-buffered and re-written only
+// after DONE of the step that used them; vals[] of step t+1 is written by pull(t+1), which every owner
+// issues after it has seen ROWV = t from everybody (all row kernels of step t have finished);
+// in_rowv of step t+1 is written after VALS = t+1 from every owner, i.e. after every push of step t.
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: the library itself is bound at run time, see XfNccl
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
+#include <string>
 #include <vector>
 
 #include "internal.h"
@@ -47,7 +55,6 @@ struct XfNccl {
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
-  decltype(&ncclCommSplit) CommSplit = nullptr;  // optional (NCCL >= 2.18)
   bool ok = false;
 };
 static XfNccl g_nccl;
@@ -70,7 +77,6 @@ static int xf_nccl_bind() {
   XF_BIND(GetUniqueId) XF_BIND(CommInitRank) XF_BIND(CommDestroy) XF_BIND(AllReduce) XF_BIND(AllGather)
   XF_BIND(Send) XF_BIND(Recv) XF_BIND(GroupStart) XF_BIND(GroupEnd) XF_BIND(GetErrorString)
 #undef XF_BIND
-  g_nccl.CommSplit = reinterpret_cast<decltype(g_nccl.CommSplit)>(dlsym(h, "ncclCommSplit"));
   g_nccl.ok = true;
   return XF_OK;
 }
@@ -86,7 +92,6 @@ static int xf_nccl_bind() {
 
 struct xf_comm {
   ncclComm_t nccl = nullptr;
-  ncclComm_t nccl2 = nullptr;  // same ranks, independent resources: bucket-size allgather of the NEXT batch
   int rank = 0, nranks = 1, device = 0;
 };
 
@@ -118,18 +123,64 @@ XF_DLL int xf_comm_create(xf_comm** out, const uint8_t id[XF_COMM_ID_BYTES], int
     delete c;
     return XF_ERR_COMM;
   }
-  if (g_nccl.CommSplit && nranks > 1) {
-    if (g_nccl.CommSplit(c->nccl, 0, rank, &c->nccl2, nullptr) != ncclSuccess) c->nccl2 = nullptr;
-  }
   *out = c;
   return XF_OK;
 }
 
 XF_DLL int xf_comm_destroy(xf_comm* c) {
   if (!c) return XF_OK;
-  if (c->nccl2) g_nccl.CommDestroy(c->nccl2);
   if (c->nccl) g_nccl.CommDestroy(c->nccl);
   delete c;
+  return XF_OK;
+}
+
+// Rendezvous through a file for launchers that have no other channel (the reference's CLI / c_api under
+// XFLOW_RANK / XFLOW_WORLD, worker.cc): rank 0 writes the id (temporary name + rename), the others wait
+// for it; rank 0 removes the file once its communicator exists, i.e. once every rank has read it.
+XF_DLL int xf_comm_create_from_file(xf_comm** out, const char* path, int rank, int nranks, int device) {
+  if (!out || !path || nranks < 1 || rank < 0 || rank >= nranks) return XF_ERR_ARG;
+  uint8_t id[XF_COMM_ID_BYTES];
+  if (rank == 0) {
+    XF_TRY(xf_comm_get_id(id));
+    std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f || fwrite(id, 1, XF_COMM_ID_BYTES, f) != XF_COMM_ID_BYTES || fclose(f) != 0 || rename(tmp.c_str(), path) != 0) {
+      xf_set_error("cannot write the communicator id to %s", path);
+      return XF_ERR_IO;
+    }
+  } else {
+    const char* to = getenv("XFLOW_RENDEZVOUS_TIMEOUT_S");
+    const int limit_ms = ((to && atoi(to) > 0) ? atoi(to) : 300) * 1000;
+    int waited = 0;
+    for (;;) {
+      FILE* f = fopen(path, "rb");
+      if (f) {
+        const size_t got = fread(id, 1, XF_COMM_ID_BYTES, f);
+        fclose(f);
+        if (got == XF_COMM_ID_BYTES) break;
+      }
+      if (waited >= limit_ms) { xf_set_error("timed out waiting for rank 0's communicator id in %s", path); return XF_ERR_COMM; }
+      usleep(20000);
+      waited += 20;
+    }
+  }
+  int rc = xf_comm_create(out, id, rank, nranks, device);
+  if (rank == 0) remove(path);
+  return rc;
+}
+
+// max over ranks of one host value (used to agree on the number of collective steps of an epoch)
+XF_DLL int xf_comm_allreduce_max(xf_comm* c, uint64_t* inout) {
+  if (!c || !inout) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaSetDevice(c->device));
+  unsigned long long* d = nullptr;
+  XF_CUDA_TRY(cudaMalloc(&d, sizeof(*d)));
+  XF_CUDA_TRY(cudaMemcpy(d, inout, sizeof(*d), cudaMemcpyHostToDevice));
+  ncclResult_t r = g_nccl.AllReduce(d, d, 1, ncclUint64, ncclMax, c->nccl, 0);
+  if (r != ncclSuccess) { cudaFree(d); xf_set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return XF_ERR_COMM; }
+  XF_CUDA_TRY(cudaStreamSynchronize(0));
+  XF_CUDA_TRY(cudaMemcpy(inout, d, sizeof(*d), cudaMemcpyDeviceToHost));
+  cudaFree(d);
   return XF_OK;
 }
 
@@ -148,225 +199,94 @@ XF_DLL int xf_comm_barrier(xf_comm* c) {
   return XF_OK;
 }
 
-// -------------------------------------------------------------------------------------------------
-// worker-side kernels of the sharded step
-// -------------------------------------------------------------------------------------------------
-#define XF_MG_MAX_SHARDS 16
-#define XF_WS_BLOCK 1024
-#define XF_WS_TOK 4  // tokens per thread
-
-__device__ __forceinline__ int xf_dev_shard_of(uint64_t key, uint64_t width, int S) {
-  const uint64_t s = key / width;
-  return (int)(s < (uint64_t)S ? s : (uint64_t)S - 1);
-}
-
-// Insert every token's key into the work set; the token that claims a key first numbers it inside
-// its owner's bucket (block-aggregated reservation: one global atomic per block and shard) and lists
-// it in ws.keys.  Buckets are contiguous: u = shard * cap + position.
-__global__ void __launch_bounds__(XF_WS_BLOCK)
-xf_k_ws_dedup(XfWorkSet ws, const uint64_t* __restrict__ keys, uint32_t nnz, uint64_t width, int S,
-              uint32_t* __restrict__ bucket_cnt) {
-  __shared__ unsigned int s_cnt[XF_MG_MAX_SHARDS];
-  __shared__ unsigned int s_base[XF_MG_MAX_SHARDS];
-  if (threadIdx.x < XF_MG_MAX_SHARDS) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t j_base = blockIdx.x * (XF_WS_BLOCK * XF_WS_TOK) + threadIdx.x;
-  uint64_t my_key[XF_WS_TOK];
-  uint64_t my_slot[XF_WS_TOK];
-  uint32_t my_local[XF_WS_TOK];  // position inside the block's share of the bucket, or NONE
-#pragma unroll
-  for (int i = 0; i < XF_WS_TOK; ++i) {
-    const uint32_t j = j_base + i * XF_WS_BLOCK;
-    my_local[i] = 0xFFFFFFFFu;
-    my_key[i] = (j < nnz) ? __ldcs(keys + j) : 0xFFFFFFFFFFFFFFFFull;
-  }
-#pragma unroll
-  for (int i = 0; i < XF_WS_TOK; ++i) {
-    const uint64_t key = my_key[i];
-    if (key == 0xFFFFFFFFFFFFFFFFull) continue;
-    uint64_t s = xf_ws_hash(key, ws.log2cap);
-    for (int probes = 0; probes < 8192; ++probes) {
-      unsigned long long* kp = reinterpret_cast<unsigned long long*>(ws.set + s * 16);
-      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
-      if (cur == 0xFFFFFFFFFFFFFFFFull) cur = atomicCAS(kp, 0xFFFFFFFFFFFFFFFFull, (unsigned long long)key);
-      if (cur == 0xFFFFFFFFFFFFFFFFull || cur == key) break;
-      s = (s + 1) & ws.mask;
-    }
-    // claim: exactly one token per key sees "unclaimed"
-    const unsigned int old = atomicExch(reinterpret_cast<unsigned int*>(ws.set + s * 16 + 12), 0u);
-    if (old == 0xFFFFFFFFu) {
-      my_slot[i] = s;
-      my_local[i] = atomicAdd(&s_cnt[xf_dev_shard_of(key, width, S)], 1u);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < S && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(bucket_cnt + threadIdx.x, s_cnt[threadIdx.x]);
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < XF_WS_TOK; ++i) {
-    if (my_local[i] == 0xFFFFFFFFu) continue;
-    const int q = xf_dev_shard_of(my_key[i], width, S);
-    const uint32_t u = (uint32_t)q * ws.cap + s_base[q] + my_local[i];
-    ws.keys[u] = my_key[i];
-    *reinterpret_cast<uint32_t*>(ws.set + my_slot[i] * 16 + 8) = u;
-  }
-}
-
-// per unique key: gradient sums / rows -> Push payload; accumulators back to zero (streaming pass)
-__global__ void xf_k_ws_grads(XfWorkSet ws, XfBucketCounts cnt, double rows, int want_grads,
-                              float* __restrict__ grad_w, float* __restrict__ grad_v) {
-  const int q = blockIdx.y;
-  const uint32_t n = cnt.c[q];
-  const int K = ws.K;
-  const uint64_t per = (uint64_t)K + 1;
-  const uint64_t total = (uint64_t)n * per;
-  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (uint64_t)gridDim.x * blockDim.x) {
-    // coordinate-major inside the bucket keeps both arrays coalesced
-    if (x < n) {
-      const uint64_t u = (uint64_t)q * ws.cap + x;
-      if (want_grads) grad_w[u] = xf_div_rows((float)ws.gw[u], rows);  // lr_worker.cc:116-118
-      ws.gw[u] = 0.0;
-    } else {
-      const uint64_t y = x - n;  // in [0, n*K)
-      const uint64_t idx = (uint64_t)q * ws.cap * K + y;
-      // latent gradient from the factorised sums: gv[u,k] = Aq[u] - v[u,k] * L[u]  (fm_worker.cc:141-142,154-156);
-      // the accumulators are cleared by the caller once every coordinate has read them
-      const uint64_t ul = y / (uint64_t)K;
-      const double2 a = __ldcg(reinterpret_cast<const double2*>(ws.acc) + ((uint64_t)q * ws.cap + ul));
-      if (want_grads) grad_v[idx] = xf_div_rows((float)(a.y - (double)ws.v[idx] * a.x), rows);
-    }
-  }
-}
 
 // -------------------------------------------------------------------------------------------------
-// host orchestration
+// sharded step: host orchestration
 // -------------------------------------------------------------------------------------------------
 struct XfMg {
-  int S = 1, rank = 0;
+  int S = 1, rank = 0, K = 0;
+  bool fm = false;
   uint64_t width = 0;
-  // Two work sets: batch b+1 is deduplicated (second stream, second communicator for its bucket-size
-  // allgather) while batch b's gradients travel and its owner updates run on the table stream.
-  XfWorkSet ws2[2];
-  size_t set_bytes = 0;
-  XfDevBuf d_set[2], d_keys[2], d_w[2], d_v[2], d_gw[2], d_acc[2], grad_w[2], grad_v[2], bucket_cnt[2], all_counts;
+  uint32_t cap = 0, max_rows = 0;
+  XfSlabLayout L;
+  uint8_t* slab = nullptr;  // this rank's slab (cudaMalloc, exported with cudaIpc)
+  XfPeers peers;            // every rank's slab as mapped here (peers.slab[rank] == slab)
+  XfDevBuf slots, tok_pos[2], bucket_cnt[2], rowv_local, touched;
+  XfDevBuf side_v;  // FM, S > 1: latent rows as pulled by the tokens of sources >= 1 (see xf_k_pull_tokens)
+  uint32_t touched_extra = 0;
   cudaStream_t st2 = nullptr;
-  cudaEvent_t ev_free[2] = {nullptr, nullptr};  // work set no longer read by the table stream
+  cudaEvent_t ev_rows_done[2] = {nullptr, nullptr};  // tok_pos[p] no longer read by the table stream
   uint64_t step_no = 0;
-  XfDevBuf recv_keys, recv_slots, resp_w, resp_v, rgrad_w, rgrad_v;   // owner side, grouped by source
-  // Peer-memory exchange (default when cudaIpc works; XFLOW_P2P=0 keeps the NCCL send/recv groups):
-  // every buffer a peer reads is exported once with cudaIpcGetMemHandle and mapped by all ranks; an
-  // exchange is then a handful of DMA reads from peer memory (cudaMemcpyAsync) behind a tiny NCCL
-  // all-reduce that orders "producer finished" across ranks on the table stream.
-  bool p2p = false;
-  enum { PEER_KEYS0 = 0, PEER_KEYS1, PEER_GW0, PEER_GW1, PEER_GV0, PEER_GV1, PEER_RESP_W, PEER_RESP_V, PEER_NBUF };
-  void* peer[XF_MG_MAX_SHARDS][PEER_NBUF];
-  int* d_barrier = nullptr;
-  uint32_t* h_counts = nullptr;        // pinned S*S
-  std::vector<uint64_t> send_off, recv_off, send_cnt, recv_cnt, own_off, resp_off;
+  unsigned long long timeout_ns = 120ull * 1000000000ull;
+  // received-token counts of recent steps, read back asynchronously: sizes the next steps' growth checks
+  uint32_t* h_meta = nullptr;  // pinned [4][XF_MG_MAX_SHARDS * 4]
+  cudaEvent_t meta_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool meta_inflight[4] = {false, false, false, false};
+  uint64_t last_recv = 0;
+  bool have_recv = false;
   // XFLOW_MG_TRACE=1: CUDA events at the phase boundaries of every step, averages printed at destroy
   bool trace = false;
   std::vector<cudaEvent_t> tev;
-  double tsum[16] = {0};
   uint64_t tsteps = 0;
 };
-static const char* kMgPhase[] = {"set clear + dedup", "counts allgather+sync", "a2a keys", "owner pull", "a2a values",
-                                 "(unused)", "fused step (work set)", "grads", "a2a grads", "owner updates"};
+enum { XF_TR_NMARK = 8 };
+static const char* kMgPhase[] = {"wait KEYS (route of this batch ran on stream 2)", "owner: pull tokens", "wait VALS",
+                                 "worker: rows + residual broadcast", "wait ROWV", "owner: push (S sources)", "signal DONE"};
 #define XF_MG_TRACE_STEPS 512
-#define XF_MG_MARK(i) do { if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) cudaEventRecord(mg->tev[mg->tsteps * 11 + (i)], st); } while (0)
+#define XF_MG_MARK(i) do { if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) cudaEventRecord(mg->tev[mg->tsteps * XF_TR_NMARK + (i)], st); } while (0)
 
-// ---- peer-memory exchange ------------------------------------------------------------------------
-static int xf_mg_barrier(xf_comm* c, XfMg* mg, cudaStream_t st) {
-  XF_NCCL_TRY(g_nccl.AllReduce(mg->d_barrier, mg->d_barrier, 1, ncclInt, ncclSum, c->nccl, st));
+static int xf_mg_nccl_barrier(xf_comm* c, int* d_word, cudaStream_t st) {
+  XF_NCCL_TRY(g_nccl.AllReduce(d_word, d_word, 1, ncclInt, ncclSum, c->nccl, st));
   return XF_OK;
 }
 
-static void* xf_mg_local_buf(XfMg* mg, int i) {
-  switch (i) {
-    case XfMg::PEER_KEYS0: return mg->d_keys[0].p;
-    case XfMg::PEER_KEYS1: return mg->d_keys[1].p;
-    case XfMg::PEER_GW0: return mg->grad_w[0].p;
-    case XfMg::PEER_GW1: return mg->grad_w[1].p;
-    case XfMg::PEER_GV0: return mg->grad_v[0].p;
-    case XfMg::PEER_GV1: return mg->grad_v[1].p;
-    case XfMg::PEER_RESP_W: return mg->resp_w.p;
-    case XfMg::PEER_RESP_V: return mg->resp_v.p;
-  }
-  return nullptr;
-}
-
-// Export this rank's exchange buffers, import everybody else's.  Any failure on any rank (no IPC in this
-// container, no peer access) leaves p2p off everywhere: the decision is agreed through an all-reduce.
-static int xf_mg_setup_p2p(xf_trainer* tr, XfMg* mg, size_t tot, size_t K) {
+// Export this rank's slab, map everybody else's.  A rank that cannot (no IPC, no peer access) makes the
+// whole creation fail on every rank: there is no slower fallback path.
+static int xf_mg_map_peers(xf_trainer* tr, XfMg* mg) {
   xf_comm* c = tr->comm;
   const int S = mg->S;
-  memset(mg->peer, 0, sizeof(mg->peer));
-  const char* e = getenv("XFLOW_P2P");
-  const bool want = !(e && *e == '0');
   cudaStream_t st = tr->table->stream;
-  XF_CUDA_TRY(cudaMalloc(&mg->d_barrier, sizeof(int)));
-  XF_CUDA_TRY(cudaMemsetAsync(mg->d_barrier, 0, sizeof(int), st));
-  // peers read the Pull responses in place: fixed size, never reallocated
-  XF_TRY(mg->resp_w.ensure(tot * 4 + 4));
-  if (K) XF_TRY(mg->resp_v.ensure(tot * 4 * K + 4));
-  struct Pack { cudaIpcMemHandle_t h[XfMg::PEER_NBUF]; int ok; int pad[15]; };
-  std::vector<Pack> all((size_t)S);
+  struct Pack { cudaIpcMemHandle_t h; uint64_t total; uint32_t cap, max_rows; int K, ok; };
   Pack mine;
   memset(&mine, 0, sizeof(mine));
-  mine.ok = want ? 1 : 0;
-  for (int i = 0; i < XfMg::PEER_NBUF && mine.ok; ++i) {
-    void* p = xf_mg_local_buf(mg, i);
-    if (p && cudaIpcGetMemHandle(&mine.h[i], p) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
-  }
+  mine.ok = cudaIpcGetMemHandle(&mine.h, mg->slab) == cudaSuccess ? 1 : 0;
+  if (!mine.ok) cudaGetLastError();
+  mine.total = mg->L.total; mine.cap = mg->cap; mine.max_rows = mg->max_rows; mine.K = mg->K;
+  std::vector<Pack> all((size_t)S);
   XfDevBuf d_all;
-  XF_TRY(d_all.ensure(sizeof(Pack) * (size_t)S));
+  XF_TRY(d_all.ensure(sizeof(Pack) * (size_t)S + 16));
   XF_CUDA_TRY(cudaMemcpyAsync((char*)d_all.p + sizeof(Pack) * (size_t)mg->rank, &mine, sizeof(Pack), cudaMemcpyHostToDevice, st));
   XF_NCCL_TRY(g_nccl.AllGather((char*)d_all.p + sizeof(Pack) * (size_t)mg->rank, d_all.p, sizeof(Pack), ncclChar, c->nccl, st));
   XF_CUDA_TRY(cudaMemcpyAsync(all.data(), d_all.p, sizeof(Pack) * (size_t)S, cudaMemcpyDeviceToHost, st));
   XF_CUDA_TRY(cudaStreamSynchronize(st));
   int ok = 1;
-  for (int q = 0; q < S; ++q) ok &= all[q].ok;
-  if (ok) {
-    for (int q = 0; q < S && ok; ++q) {
-      if (q == mg->rank) continue;
-      for (int i = 0; i < XfMg::PEER_NBUF && ok; ++i) {
-        if (!xf_mg_local_buf(mg, i)) continue;  // same set of buffers on every rank
-        if (cudaIpcOpenMemHandle(&mg->peer[q][i], all[q].h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-          cudaGetLastError();
-          mg->peer[q][i] = nullptr;
-          ok = 0;
-        }
-      }
+  for (int q = 0; q < S; ++q) {
+    ok &= all[q].ok;
+    if (all[q].total != mine.total || all[q].cap != mine.cap || all[q].max_rows != mine.max_rows || all[q].K != mine.K) ok = 0;
+  }
+  memset(&mg->peers, 0, sizeof(mg->peers));
+  mg->peers.slab[mg->rank] = mg->slab;
+  for (int q = 0; q < S && ok; ++q) {
+    if (q == mg->rank) continue;
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
     }
+    mg->peers.slab[q] = (uint8_t*)p;
   }
-  // agree on the outcome
+  // agree on the outcome (sum of failures)
+  int* d_word = (int*)d_all.p;
   int flag = ok ? 0 : 1;
-  XF_CUDA_TRY(cudaMemcpyAsync(mg->d_barrier, &flag, sizeof(int), cudaMemcpyHostToDevice, st));
-  XF_TRY(xf_mg_barrier(c, mg, st));
-  XF_CUDA_TRY(cudaMemcpyAsync(&flag, mg->d_barrier, sizeof(int), cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaMemcpyAsync(d_word, &flag, sizeof(int), cudaMemcpyHostToDevice, st));
+  XF_TRY(xf_mg_nccl_barrier(c, d_word, st));
+  XF_CUDA_TRY(cudaMemcpyAsync(&flag, d_word, sizeof(int), cudaMemcpyDeviceToHost, st));
   XF_CUDA_TRY(cudaStreamSynchronize(st));
-  XF_CUDA_TRY(cudaMemsetAsync(mg->d_barrier, 0, sizeof(int), st));
   d_all.release();
-  mg->p2p = (flag == 0);
-  if (!mg->p2p) {
-    for (int q = 0; q < S; ++q)
-      for (int i = 0; i < XfMg::PEER_NBUF; ++i)
-        if (mg->peer[q][i]) { cudaIpcCloseMemHandle(mg->peer[q][i]); mg->peer[q][i] = nullptr; }
-  }
-  if (getenv("XFLOW_MG_TRACE")) fprintf(stderr, "[xflow mg] rank %d: peer-memory exchange %s\n", mg->rank, mg->p2p ? "on" : "off (NCCL send/recv)");
-  return XF_OK;
-}
-
-// One exchange as peer reads: segment q of `dst` (element offset doff[q], cnt[q] keys) is copied from rank
-// q's exported buffer `which`, where it starts at element offset soff[q].  The caller has already ordered
-// "rank q finished writing" before this point of the stream (bucket-size allgather or xf_mg_barrier).
-static int xf_mg_pull(XfMg* mg, int which, const void* local_src, const std::vector<uint64_t>& soff, void* dst,
-                      const std::vector<uint64_t>& doff, const std::vector<uint64_t>& cnt, size_t bytes_per_key,
-                      cudaStream_t st) {
-  for (int q = 0; q < mg->S; ++q) {
-    if (!cnt[q]) continue;
-    const char* src = (q == mg->rank) ? (const char*)local_src : (const char*)mg->peer[q][which];
-    XF_CUDA_TRY(cudaMemcpyAsync((char*)dst + doff[q] * bytes_per_key, src + soff[q] * bytes_per_key, cnt[q] * bytes_per_key,
-                                cudaMemcpyDeviceToDevice, st));
+  if (flag != 0) {
+    xf_set_error("sharded trainer: cudaIpc peer mapping failed or trainer configurations differ between ranks "
+                 "(%d rank(s) reported a problem; all ranks need the same max_rows / max_nnz / model)", flag);
+    return XF_ERR_COMM;
   }
   return XF_OK;
 }
@@ -374,316 +294,253 @@ static int xf_mg_pull(XfMg* mg, int which, const void* local_src, const std::vec
 int xf_mg_create(xf_trainer* tr) {
   xf_comm* c = tr->comm;
   XfMg* mg = new XfMg;
+  tr->mg = mg;
   mg->S = c->nranks;
   mg->rank = c->rank;
   if (mg->S > XF_MG_MAX_SHARDS) {
     xf_set_error("at most %d shards supported", XF_MG_MAX_SHARDS);
-    delete mg;
+    delete mg; tr->mg = nullptr;
     return XF_ERR_ARG;
   }
   const int S = mg->S;
-  mg->width = 0xFFFFFFFFFFFFFFFFull / (uint64_t)S;
-  const uint32_t nnz = tr->cfg.max_nnz;
-  const size_t K = (size_t)tr->table->view.K;
-  uint64_t cap_set = 1024;
-  while (cap_set < 2ull * nnz) cap_set <<= 1;  // load factor <= 0.5
-  uint32_t lg = 0;
-  while ((1ull << lg) < cap_set) ++lg;
-  mg->set_bytes = cap_set * 16;
-  const size_t tot = (size_t)S * nnz;  // bucket-major arrays, bucket stride = max_nnz
+  mg->width = 0xFFFFFFFFFFFFFFFFull / (uint64_t)S;  // postoffice.cc:138-140
+  mg->cap = tr->cfg.max_nnz;                        // a (source, owner) segment can hold a whole batch
+  mg->max_rows = tr->cfg.max_rows;
+  mg->K = tr->table->view.K;
+  mg->fm = mg->K > 0;
+  mg->L = xf_slab_layout(S, mg->cap, mg->max_rows, mg->fm);
+  const char* to = getenv("XFLOW_MG_TIMEOUT_S");
+  if (to && atoi(to) > 0) mg->timeout_ns = (unsigned long long)atoi(to) * 1000000000ull;
   cudaStream_t st = tr->table->stream;
-  XF_CUDA_TRY(cudaStreamCreateWithFlags(&mg->st2, cudaStreamNonBlocking));
-  for (int b = 0; b < 2; ++b) {
-    XF_TRY(mg->d_set[b].ensure(mg->set_bytes));
-    XF_TRY(mg->d_keys[b].ensure(tot * 8));
-    XF_TRY(mg->d_w[b].ensure(tot * 4));
-    XF_TRY(mg->d_gw[b].ensure(tot * 8));
-    XF_TRY(mg->grad_w[b].ensure(tot * 4));
-    if (K) {
-      XF_TRY(mg->d_v[b].ensure(tot * 4 * K));
-      XF_TRY(mg->d_acc[b].ensure(tot * 16));
-      XF_TRY(mg->grad_v[b].ensure(tot * 4 * K));
+  int rc = XF_OK;
+  do {
+    if (cudaMalloc(&mg->slab, mg->L.total) != cudaSuccess) { cudaGetLastError(); xf_set_error("cannot allocate the %llu-byte exchange slab", (unsigned long long)mg->L.total); rc = XF_ERR_CUDA; break; }
+    // flags, meta and counters start at zero; the rest is written before it is read
+    if (cudaMemsetAsync(mg->slab, 0, mg->L.off_in_keys, st) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&mg->st2, cudaStreamNonBlocking, lo) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
+    if ((rc = mg->slots.ensure((size_t)S * mg->cap * 4)) != XF_OK) break;
+    if ((rc = mg->rowv_local.ensure((size_t)mg->max_rows * 8 + 16)) != XF_OK) break;
+    const bool lazy = tr->table->view.lazy != 0;
+    if (!lazy) {
+      mg->touched_extra = xf_acc_touched_extra(mg->K, (uint64_t)mg->cap);
+      if ((rc = mg->touched.ensure(((size_t)mg->cap + 2 * (size_t)mg->touched_extra) * 4)) != XF_OK) break;
+      if (mg->fm && S > 1 && (rc = mg->side_v.ensure((size_t)S * mg->cap * (size_t)mg->K * 4)) != XF_OK) break;
     }
-    XF_TRY(mg->bucket_cnt[b].ensure((size_t)S * 4));
-    XF_CUDA_TRY(cudaMemsetAsync(mg->d_gw[b].p, 0, tot * 8, st));
-    if (K) XF_CUDA_TRY(cudaMemsetAsync(mg->d_acc[b].p, 0, tot * 16, st));
-    XF_CUDA_TRY(cudaEventCreateWithFlags(&mg->ev_free[b], cudaEventDisableTiming));
-    XfWorkSet& w = mg->ws2[b];
-    w.set = mg->d_set[b].as<uint8_t>();
-    w.mask = cap_set - 1;
-    w.log2cap = lg;
-    w.cap = nnz;
-    w.K = (int)K;
-    w.keys = mg->d_keys[b].as<uint64_t>();
-    w.w = mg->d_w[b].as<float>();
-    w.v = K ? mg->d_v[b].as<float>() : nullptr;
-    w.gw = mg->d_gw[b].as<double>();
-    w.acc = K ? mg->d_acc[b].as<double>() : nullptr;
+    for (int b = 0; b < 2 && rc == XF_OK; ++b) {
+      if ((rc = mg->tok_pos[b].ensure((size_t)mg->cap * 4 + 16)) != XF_OK) break;
+      if ((rc = mg->bucket_cnt[b].ensure(XF_MG_MAX_SHARDS * 4)) != XF_OK) break;
+      if (cudaEventCreateWithFlags(&mg->ev_rows_done[b], cudaEventDisableTiming) != cudaSuccess) rc = XF_ERR_CUDA;
+    }
+    if (rc != XF_OK) break;
+    if (cudaHostAlloc(&mg->h_meta, 4 * XF_MG_MAX_SHARDS * 4 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
+    for (int i = 0; i < 4; ++i)
+      if (cudaEventCreateWithFlags(&mg->meta_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = XF_ERR_CUDA;
+    if (rc != XF_OK) break;
+    if (cudaStreamSynchronize(st) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
+    const char* tenv = getenv("XFLOW_MG_TRACE");
+    mg->trace = tenv && *tenv == '1';
+    if (mg->trace) {
+      mg->tev.resize((size_t)XF_TR_NMARK * XF_MG_TRACE_STEPS);
+      for (auto& e : mg->tev) cudaEventCreate(&e);
+    }
+    rc = xf_mg_map_peers(tr, mg);
+  } while (0);
+  if (rc != XF_OK) {
+    if (rc == XF_ERR_CUDA) xf_set_error("CUDA error while creating the sharded trainer: %s", cudaGetErrorString(cudaGetLastError()));
+    xf_mg_destroy(tr);
+    return rc;
   }
-  XF_TRY(mg->all_counts.ensure((size_t)S * S * 4));
-  XF_CUDA_TRY(cudaStreamSynchronize(st));
-  XF_CUDA_TRY(cudaHostAlloc(&mg->h_counts, (size_t)S * S * 4, cudaHostAllocDefault));
-  mg->send_off.resize(S + 1);
-  mg->recv_off.resize(S + 1);
-  mg->send_cnt.resize(S);
-  mg->recv_cnt.resize(S);
-  mg->own_off.resize(S);
-  mg->resp_off.resize(S);
-  const char* tenv = getenv("XFLOW_MG_TRACE");
-  mg->trace = tenv && *tenv == '1';
-  if (mg->trace) {
-    mg->tev.resize(11 * XF_MG_TRACE_STEPS);
-    for (auto& e : mg->tev) cudaEventCreate(&e);
-  }
-  tr->mg = mg;
-  int rc = xf_mg_setup_p2p(tr, mg, tot, K);
-  if (rc != XF_OK) { xf_mg_destroy(tr); return rc; }
   return XF_OK;
 }
 
 void xf_mg_destroy(xf_trainer* tr) {
   XfMg* mg = (XfMg*)tr->mg;
   if (!mg) return;
+  cudaStream_t st = tr->table->stream;
+  if (mg->st2) cudaStreamSynchronize(mg->st2);
+  cudaStreamSynchronize(st);
   if (mg->trace && mg->tsteps) {
-    cudaDeviceSynchronize();
     // skip the first steps (population / allocation); events were recorded without any extra sync
     const uint64_t skip = mg->tsteps > 40 ? 30 : 0;
+    double tsum[XF_TR_NMARK] = {0};
     for (uint64_t t = skip; t < mg->tsteps; ++t)
-      for (int i = 0; i < 10; ++i) {
+      for (int i = 0; i + 1 < XF_TR_NMARK; ++i) {
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, mg->tev[t * 11 + i], mg->tev[t * 11 + i + 1]);
-        mg->tsum[i] += ms;
+        cudaEventElapsedTime(&ms, mg->tev[t * XF_TR_NMARK + i], mg->tev[t * XF_TR_NMARK + i + 1]);
+        tsum[i] += ms;
       }
     const double n = (double)(mg->tsteps - skip);
-    fprintf(stderr, "[xflow mg trace] rank %d, steps %llu..%llu, mean ms per phase:\n", mg->rank,
-            (unsigned long long)skip, (unsigned long long)mg->tsteps);
+    fprintf(stderr, "[xflow mg trace] rank %d of %d, steps %llu..%llu, mean ms per phase on the table stream:\n", mg->rank,
+            mg->S, (unsigned long long)skip, (unsigned long long)mg->tsteps);
     double tot = 0;
-    for (int i = 0; i < 10; ++i) { fprintf(stderr, "    %-24s %8.4f\n", kMgPhase[i], mg->tsum[i] / n); tot += mg->tsum[i] / n; }
-    fprintf(stderr, "    %-24s %8.4f\n", "total", tot);
+    for (int i = 0; i + 1 < XF_TR_NMARK; ++i) { fprintf(stderr, "    %-52s %8.4f\n", kMgPhase[i], tsum[i] / n); tot += tsum[i] / n; }
+    fprintf(stderr, "    %-52s %8.4f\n", "total", tot);
   }
-  cudaStreamSynchronize(mg->st2);
-  if (mg->p2p) {
-    // unmap the peers' buffers, then make sure every rank has done so before anybody frees its own
-    cudaStreamSynchronize(tr->table->stream);
-    for (int q = 0; q < mg->S; ++q)
-      for (int i = 0; i < XfMg::PEER_NBUF; ++i)
-        if (mg->peer[q][i]) cudaIpcCloseMemHandle(mg->peer[q][i]);
-    if (xf_mg_barrier(tr->comm, mg, tr->table->stream) == XF_OK) cudaStreamSynchronize(tr->table->stream);
+  // nobody may still be storing into a slab that is about to be unmapped / freed
+  bool mapped = false;
+  for (int q = 0; q < mg->S; ++q) mapped |= (q != mg->rank && mg->peers.slab[q] != nullptr);
+  if (mapped) {
+    int* d_word = nullptr;
+    if (cudaMalloc(&d_word, sizeof(int)) == cudaSuccess) {
+      cudaMemsetAsync(d_word, 0, sizeof(int), st);
+      if (xf_mg_nccl_barrier(tr->comm, d_word, st) == XF_OK) cudaStreamSynchronize(st);
+      for (int q = 0; q < mg->S; ++q)
+        if (q != mg->rank && mg->peers.slab[q]) cudaIpcCloseMemHandle(mg->peers.slab[q]);
+      if (xf_mg_nccl_barrier(tr->comm, d_word, st) == XF_OK) cudaStreamSynchronize(st);
+      cudaFree(d_word);
+    }
   }
-  if (mg->d_barrier) cudaFree(mg->d_barrier);
+  if (mg->slab) cudaFree(mg->slab);
+  mg->slots.release(); mg->rowv_local.release(); mg->touched.release(); mg->side_v.release();
   for (int b = 0; b < 2; ++b) {
-    XfDevBuf* pb[] = {&mg->d_set[b], &mg->d_keys[b], &mg->d_w[b], &mg->d_v[b], &mg->d_gw[b], &mg->d_acc[b],
-                      &mg->grad_w[b], &mg->grad_v[b], &mg->bucket_cnt[b]};
-    for (XfDevBuf* x : pb) x->release();
-    if (mg->ev_free[b]) cudaEventDestroy(mg->ev_free[b]);
+    mg->tok_pos[b].release(); mg->bucket_cnt[b].release();
+    if (mg->ev_rows_done[b]) cudaEventDestroy(mg->ev_rows_done[b]);
   }
-  XfDevBuf* bufs[] = {&mg->all_counts, &mg->recv_keys, &mg->recv_slots, &mg->resp_w, &mg->resp_v, &mg->rgrad_w, &mg->rgrad_v};
-  for (XfDevBuf* b : bufs) b->release();
+  for (int i = 0; i < 4; ++i) if (mg->meta_ev[i]) cudaEventDestroy(mg->meta_ev[i]);
+  if (mg->h_meta) cudaFreeHost(mg->h_meta);
   if (mg->st2) cudaStreamDestroy(mg->st2);
-  if (mg->h_counts) cudaFreeHost(mg->h_counts);
   for (auto& e : mg->tev) cudaEventDestroy(e);
   delete mg;
   tr->mg = nullptr;
 }
 
-// grouped all-to-all: bucket q of `send` (element offset soff[q], scnt[q] keys) goes to rank q, segment q
-// of `recv` comes from rank q.  `scale` = items of `elem_bytes` per key.
-static int xf_all_to_all(xf_comm* c, const void* send, const std::vector<uint64_t>& soff,
-                         const std::vector<uint64_t>& scnt, void* recv, const std::vector<uint64_t>& roff,
-                         const std::vector<uint64_t>& rcnt, size_t elem_bytes, size_t scale, cudaStream_t st) {
-  XF_NCCL_TRY(g_nccl.GroupStart());
-  for (int q = 0; q < c->nranks; ++q) {
-    if (scnt[q])
-      XF_NCCL_TRY(g_nccl.Send((const char*)send + soff[q] * scale * elem_bytes, scnt[q] * scale * elem_bytes, ncclChar, q,
-                              c->nccl, st));
-    if (rcnt[q])
-      XF_NCCL_TRY(g_nccl.Recv((char*)recv + roff[q] * scale * elem_bytes, rcnt[q] * scale * elem_bytes, ncclChar, q,
-                              c->nccl, st));
-  }
-  XF_NCCL_TRY(g_nccl.GroupEnd());
+// unique keys of this rank's batches, as counted by the owners (remote atomics into our slab)
+int xf_mg_unique(xf_trainer* tr, unsigned long long* out) {
+  XfMg* mg = (XfMg*)tr->mg;
+  XF_CUDA_TRY(cudaMemcpyAsync(out, mg->slab + mg->L.off_uniq, sizeof(*out), cudaMemcpyDeviceToHost, tr->table->stream));
+  XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
   return XF_OK;
 }
 
-// Where everything of one step's three exchanges lives, from the S x S matrix counts[p*S+q] = number of
-// unique keys of worker p's batch owned by q (every rank holds the whole matrix after the allgather).
-// Element offsets ("keys"); all bucket-major arrays of a worker have bucket stride `cap`.
-//   send_off/send_cnt[q]  my bucket q: what I request from / push to owner q (and where its answers land)
-//   recv_off/recv_cnt[q]  where source q's keys / gradients land in my owner-side arrays (grouped by source)
-//   own_off[q]            where my share starts inside WORKER q's arrays   (peer reads of keys and gradients)
-//   resp_off[q]           where my answers start inside OWNER q's response arrays (peer reads of values)
-XF_DLL int xf_exchange_plan(const uint32_t* counts, int S, int rank, uint64_t cap, uint64_t* send_off,
-                            uint64_t* send_cnt, uint64_t* recv_off, uint64_t* recv_cnt, uint64_t* own_off,
-                            uint64_t* resp_off) {
-  if (!counts || S < 1 || rank < 0 || rank >= S || !send_off || !send_cnt || !recv_off || !recv_cnt || !own_off ||
-      !resp_off)
-    return XF_ERR_ARG;
-  uint64_t n_recv = 0;
-  for (int q = 0; q < S; ++q) {
-    send_cnt[q] = counts[rank * S + q];  // my keys owned by q
-    recv_cnt[q] = counts[q * S + rank];  // q's keys owned by me
-    send_off[q] = (uint64_t)q * cap;     // bucket-major work-set arrays
-    recv_off[q] = n_recv;
-    n_recv += recv_cnt[q];
-    own_off[q] = (uint64_t)rank * cap;   // bucket `rank` of worker q
-    uint64_t before = 0;                 // owner q answers its sources in rank order
-    for (int p = 0; p < rank; ++p) before += counts[p * S + q];
-    resp_off[q] = before;
-  }
-  return XF_OK;
+// How many tokens this owner should expect in the coming step: the last total it has seen arrive (read
+// back asynchronously, 1-2 steps old) with a margin, never less than twice its own batch.  Only the
+// growth check uses it; a shard that receives far more than that in a single step while nearly full
+// reports XF_ERR_FULL instead of growing (murmur-hashed keys spread evenly over the ranges).
+static uint64_t xf_mg_expected_tokens(XfMg* mg, uint32_t nnz_local) {
+  for (int i = 0; i < 4; ++i)
+    if (mg->meta_inflight[i] && cudaEventQuery(mg->meta_ev[i]) == cudaSuccess) {
+      mg->meta_inflight[i] = false;
+      uint64_t tot = 0;
+      for (int s = 0; s < mg->S; ++s) tot += mg->h_meta[(size_t)i * XF_MG_MAX_SHARDS * 4 + (size_t)s * 4];
+      mg->last_recv = tot;
+      mg->have_recv = true;
+    }
+  cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
+  uint64_t est = 2ull * nnz_local + 65536;
+  if (mg->have_recv && mg->last_recv + mg->last_recv / 4 + 65536 > est) est = mg->last_recv + mg->last_recv / 4 + 65536;
+  return est;
 }
 
 int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys, const uint8_t* d_labels,
                uint32_t rows, uint32_t nnz, int mode, float* d_abs, cudaEvent_t* pm) {
   XfMg* mg = (XfMg*)tr->mg;
-  xf_comm* c = tr->comm;
   xf_table* t = tr->table;
-  cudaStream_t st = t->stream;
-  const int S = mg->S;
-  const size_t K = (size_t)t->view.K;
-  const int cur = (int)(mg->step_no++ & 1);
-  const XfWorkSet& ws = mg->ws2[cur];
-  // With a second communicator the dedup of this batch and its bucket-size allgather run on their own
-  // stream, concurrently with whatever the previous step still has queued on the table stream
-  // (gradient exchange, owner updates).  Without it everything stays on the table stream.
-  const bool overlap = c->nccl2 != nullptr;
-  cudaStream_t sd = overlap ? mg->st2 : st;
-  ncclComm_t cd = overlap ? c->nccl2 : c->nccl;
+  cudaStream_t st = t->stream, sd = mg->st2;
+  const int S = mg->S, me = mg->rank;
+  const XfSlabLayout& L = mg->L;
+  const uint64_t step = ++mg->step_no;
+  const int p = (int)(step & 1);
+  const uint32_t cap = mg->cap;
+  uint64_t* flags = reinterpret_cast<uint64_t*>(mg->slab + L.off_flags);
+  uint32_t* meta_p = reinterpret_cast<uint32_t*>(mg->slab + L.off_meta) + (size_t)p * XF_MG_MAX_SHARDS * 4;
+  const uint64_t off_keys_p = L.off_in_keys + (uint64_t)p * S * cap * 8;
+  const uint64_t off_rows_p = L.off_in_rows + (uint64_t)p * S * cap * 4;
+  uint32_t* bucket = mg->bucket_cnt[p].as<uint32_t>();
+  uint32_t* tok_pos = mg->tok_pos[p].as<uint32_t>();
 
-  // ---- worker: clear the set (one streaming memset), dedup + number + bucket by owner
-  if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) cudaEventRecord(mg->tev[mg->tsteps * 11 + 0], sd);
-  if (overlap) {
-    XF_CUDA_TRY(cudaStreamWaitEvent(sd, mg->ev_free[cur], 0));
-    // the batch itself may still be on its way (host path: H2D on the trainer's copy stream)
-    if (tr->input_ready) XF_CUDA_TRY(cudaStreamWaitEvent(sd, tr->input_ready, 0));
-  }
+  // ---- stream 2: route this batch's tokens to their owners (overlaps the previous step's tail)
+  XF_CUDA_TRY(cudaStreamWaitEvent(sd, mg->ev_rows_done[p], 0));           // tok_pos[p] free (rows of step t-2)
+  if (tr->input_ready) XF_CUDA_TRY(cudaStreamWaitEvent(sd, tr->input_ready, 0));  // host path: H2D of this batch
   tr->input_ready = nullptr;
-  XF_CUDA_TRY(cudaMemsetAsync(mg->d_set[cur].p, 0xFF, mg->set_bytes, sd));
-  XF_CUDA_TRY(cudaMemsetAsync(mg->bucket_cnt[cur].p, 0, (size_t)S * 4, sd));
-  if (nnz) {
-    const uint32_t per_block = XF_WS_BLOCK * XF_WS_TOK;
-    xf_k_ws_dedup<<<(nnz + per_block - 1) / per_block, XF_WS_BLOCK, 0, sd>>>(ws, d_keys, nnz, mg->width, S,
-                                                                              mg->bucket_cnt[cur].as<uint32_t>());
-    ++tr->launches;
-  }
-  // ---- bucket sizes of every rank (the only host sync of the step)
-  if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) cudaEventRecord(mg->tev[mg->tsteps * 11 + 1], sd);
-  XF_NCCL_TRY(g_nccl.AllGather(mg->bucket_cnt[cur].p, mg->all_counts.p, (size_t)S, ncclUint32, cd, sd));
-  XF_CUDA_TRY(cudaMemcpyAsync(mg->h_counts, mg->all_counts.p, (size_t)S * S * 4, cudaMemcpyDeviceToHost, sd));
-  XF_CUDA_TRY(cudaStreamSynchronize(sd));
-  XF_TRY(xf_exchange_plan(mg->h_counts, S, mg->rank, ws.cap, mg->send_off.data(), mg->send_cnt.data(), mg->recv_off.data(),
-                          mg->recv_cnt.data(), mg->own_off.data(), mg->resp_off.data()));
-  uint64_t n_send = 0, n_recv = 0;
-  XfBucketCounts bc;
-  memset(&bc, 0, sizeof(bc));
-  uint32_t max_bucket = 0;
-  for (int q = 0; q < S; ++q) {
-    bc.c[q] = (uint32_t)mg->send_cnt[q];
-    if (bc.c[q] > max_bucket) max_bucket = bc.c[q];
-    n_send += mg->send_cnt[q];
-    n_recv += mg->recv_cnt[q];
-  }
-  XF_TRY(mg->recv_keys.ensure(n_recv * 8 + 8));
-  XF_TRY(mg->recv_slots.ensure(n_recv * 4 + 4));
-  XF_TRY(mg->resp_w.ensure(n_recv * 4 + 4));
-  XF_TRY(mg->rgrad_w.ensure(n_recv * 4 + 4));
-  if (K) {
-    XF_TRY(mg->resp_v.ensure(n_recv * 4 * K + 4));
-    XF_TRY(mg->rgrad_v.ensure(n_recv * 4 * K + 4));
-  }
+  if (step > 2) xf_launch_wait(flags + (size_t)XF_F_DONE * XF_MG_MAX_SHARDS, S, step - 2, t->d_error, mg->timeout_ns, sd);
+  XF_CUDA_TRY(cudaMemsetAsync(bucket, 0, XF_MG_MAX_SHARDS * 4, sd));
+  xf_launch_route(d_row_ptr, d_keys, rows, nnz, mg->width, S, me, cap, mg->peers, off_keys_p, off_rows_p, bucket, tok_pos, sd);
+  xf_launch_signal(mg->peers, L, S, me, XF_F_KEYS, step, p, bucket, rows, sd);
+  tr->launches += 3;
 
-  std::vector<uint64_t>& own_off = mg->own_off;
-  std::vector<uint64_t>& resp_off = mg->resp_off;
-
-  // ---- all-to-all #1: keys to their owners (the Pull request, kv_app.h:147-165)
-  XF_MG_MARK(2);
-  if (mg->p2p) {
-    // every rank's dedup finished before its bucket sizes left (allgather above): read the keys in place
-    XF_TRY(xf_mg_pull(mg, cur ? XfMg::PEER_KEYS1 : XfMg::PEER_KEYS0, ws.keys, own_off, mg->recv_keys.p, mg->recv_off,
-                      mg->recv_cnt, 8, st));
-  } else {
-    XF_TRY(xf_all_to_all(c, ws.keys, mg->send_off, mg->send_cnt, mg->recv_keys.p, mg->recv_off, mg->recv_cnt, 8, 1, st));
-  }
-  // ---- owner: Pull handler on this shard (insert-on-pull, ftrl.h:56,114-120)
-  XF_MG_MARK(3);
-  if (n_recv) {
-    XF_TRY(t->ensure_room(n_recv));
-    xf_launch_probe(t->view, mg->recv_keys.as<uint64_t>(), n_recv, true, mg->recv_slots.as<uint32_t>(),
-                    mg->resp_w.as<float>(), st);
-    ++tr->launches;
-    if (K) {
-      xf_launch_gather_v(t->view, mg->recv_slots.as<uint32_t>(), mg->recv_keys.as<uint64_t>(), n_recv,
-                         mg->resp_v.as<float>(), st);
-      ++tr->launches;
+  // ---- table stream, owner: Pull handler over everything routed here
+  XF_TRY(t->ensure_room(xf_mg_expected_tokens(mg, nnz)));
+  XF_MG_MARK(0);
+  xf_launch_wait(flags + (size_t)XF_F_KEYS * XF_MG_MAX_SHARDS, S, step, t->d_error, mg->timeout_ns, st);
+  if (step > 1) xf_launch_wait(flags + (size_t)XF_F_ROWV * XF_MG_MAX_SHARDS, S, step - 1, t->d_error, mg->timeout_ns, st);
+  XF_MG_MARK(1);
+  if (pm) XF_CUDA_TRY(cudaEventRecord(pm[0], st));
+  xf_launch_pull_tokens(t->view, reinterpret_cast<const uint64_t*>(mg->slab + off_keys_p), meta_p, S, me, cap,
+                        (uint64_t)nnz + 1, mg->peers, L.off_vals, mg->slots.as<uint32_t>(),
+                        (mode == 0 && mg->side_v.p) ? mg->side_v.as<float>() : nullptr, st);
+  if (pm) XF_CUDA_TRY(cudaEventRecord(pm[1], st));
+  {
+    const int slot = (int)(step & 3);
+    if (!mg->meta_inflight[slot]) {
+      XF_CUDA_TRY(cudaMemcpyAsync(mg->h_meta + (size_t)slot * XF_MG_MAX_SHARDS * 4, meta_p, XF_MG_MAX_SHARDS * 4 * sizeof(uint32_t),
+                                  cudaMemcpyDeviceToHost, st));
+      XF_CUDA_TRY(cudaEventRecord(mg->meta_ev[slot], st));
+      mg->meta_inflight[slot] = true;
     }
   }
-  // ---- all-to-all #2: values back, straight into the work set (the Pull response)
+  xf_launch_signal(mg->peers, L, S, me, XF_F_VALS, step, p, nullptr, 0, st);
+  tr->launches += 4;
+
+  // ---- worker: per-row sums, sigmoid, residual against the answers in vals[]
+  XF_MG_MARK(2);
+  xf_launch_wait(flags + (size_t)XF_F_VALS * XF_MG_MAX_SHARDS, S, step, t->d_error, mg->timeout_ns, st);
+  XF_MG_MARK(3);
+  xf_launch_rows(mg->fm, d_row_ptr, d_labels, (int)rows, mode, tok_pos, mg->slab + L.off_vals, mg->rowv_local.as<float>(),
+                 (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
+                 mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
+  XF_CUDA_TRY(cudaEventRecord(mg->ev_rows_done[p], st));
+  const uint32_t rowv_words = mg->fm ? 2 : 1;
+  if (mode == 0)
+    xf_launch_bcast_rowv(mg->rowv_local.as<float>(), rows * rowv_words, S, mg->peers, L.off_in_rowv,
+                         (uint64_t)me * mg->max_rows * rowv_words, st);
+  xf_launch_signal(mg->peers, L, S, me, XF_F_ROWV, step, p, nullptr, 0, st);
+  tr->launches += 4;
   XF_MG_MARK(4);
-  if (mg->p2p) {
-    XF_TRY(xf_mg_barrier(c, mg, st));  // every owner has answered
-    XF_TRY(xf_mg_pull(mg, XfMg::PEER_RESP_W, mg->resp_w.p, resp_off, ws.w, mg->send_off, mg->send_cnt, 4, st));
-    if (K) XF_TRY(xf_mg_pull(mg, XfMg::PEER_RESP_V, mg->resp_v.p, resp_off, ws.v, mg->send_off, mg->send_cnt, 4 * K, st));
-  } else {
-    XF_TRY(xf_all_to_all(c, mg->resp_w.p, mg->recv_off, mg->recv_cnt, ws.w, mg->send_off, mg->send_cnt, 4, 1, st));
-    if (K) XF_TRY(xf_all_to_all(c, mg->resp_v.p, mg->recv_off, mg->recv_cnt, ws.v, mg->send_off, mg->send_cnt, 4, K, st));
-  }
-
-  // ---- worker: forward / residual / gradient accumulation against the work set
-  XF_MG_MARK(5);
-  XF_MG_MARK(6);
-  if (pm) XF_CUDA_TRY(cudaEventRecord(pm[0], st));
-  xf_launch_step_ws(ws, d_row_ptr, d_keys, d_labels, (int)rows, mode,
-                    (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
-                    mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
-  if (pm) XF_CUDA_TRY(cudaEventRecord(pm[1], st));
-  ++tr->launches;
-  XF_MG_MARK(7);
   if (mode != 0) {
-    // peers may still be reading this rank's responses: nobody starts the next Pull before all are done
-    if (mg->p2p) XF_TRY(xf_mg_barrier(c, mg, st));
-    XF_CUDA_TRY(cudaEventRecord(mg->ev_free[cur], st));
-    XF_CUDA_TRY(cudaGetLastError());
-    return XF_OK;  // forward only: nothing was accumulated
-  }
-  if (n_send) {
-    dim3 grid((unsigned)xf_grid_for((uint64_t)max_bucket * (K + 1), 256, 4), (unsigned)S);
-    xf_k_ws_grads<<<grid, 256, 0, st>>>(ws, bc, (double)rows, 1, mg->grad_w[cur].as<float>(),
-                                        K ? mg->grad_v[cur].as<float>() : nullptr);
+    // forward only: nothing to push; the routed tokens are no longer needed
+    XF_MG_MARK(5);
+    XF_MG_MARK(6);
+    xf_launch_signal(mg->peers, L, S, me, XF_F_DONE, step, p, nullptr, 0, st);
     ++tr->launches;
-    // {L, Aq} of the used part of every bucket back to zero (one strided memset)
-    if (K) XF_CUDA_TRY(cudaMemset2DAsync(ws.acc, (size_t)ws.cap * 16, 0, (size_t)max_bucket * 16, (size_t)S, st));
+    if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) { cudaEventRecord(mg->tev[mg->tsteps * XF_TR_NMARK + 7], st); ++mg->tsteps; }
+    XF_CUDA_TRY(cudaGetLastError());
+    return XF_OK;
   }
 
-  // ---- all-to-all #3: gradients to the owners (the Push, kv_app.h:110-118)
-  XF_MG_MARK(8);
-  if (mg->p2p) {
-    XF_TRY(xf_mg_barrier(c, mg, st));  // every worker's gradients are final
-    XF_TRY(xf_mg_pull(mg, cur ? XfMg::PEER_GW1 : XfMg::PEER_GW0, mg->grad_w[cur].p, own_off, mg->rgrad_w.p, mg->recv_off,
-                      mg->recv_cnt, 4, st));
-    if (K)
-      XF_TRY(xf_mg_pull(mg, cur ? XfMg::PEER_GV1 : XfMg::PEER_GV0, mg->grad_v[cur].p, own_off, mg->rgrad_v.p, mg->recv_off,
-                        mg->recv_cnt, 4 * K, st));
-  } else {
-    XF_TRY(xf_all_to_all(c, mg->grad_w[cur].p, mg->send_off, mg->send_cnt, mg->rgrad_w.p, mg->recv_off, mg->recv_cnt, 4, 1, st));
-    if (K)
-      XF_TRY(xf_all_to_all(c, mg->grad_v[cur].p, mg->send_off, mg->send_cnt, mg->rgrad_v.p, mg->recv_off, mg->recv_cnt, 4, K, st));
-  }
-  XF_CUDA_TRY(cudaEventRecord(mg->ev_free[cur], st));  // work set `cur` and its gradient buffers are free again
   // ---- owner: Push handler, one optimizer step per (source, key), sources in rank order
-  XF_MG_MARK(9);
+  xf_launch_wait(flags + (size_t)XF_F_ROWV * XF_MG_MAX_SHARDS, S, step, t->d_error, mg->timeout_ns, st);
+  XF_MG_MARK(5);
   if (pm) XF_CUDA_TRY(cudaEventRecord(pm[2], st));
-  for (int q = 0; q < S; ++q) {
-    if (!mg->recv_cnt[q]) continue;
-    const uint64_t off = mg->recv_off[q];
-    xf_launch_update_pushed(t->view, mg->recv_slots.as<uint32_t>() + off, mg->recv_cnt[q],
-                            mg->rgrad_w.as<float>() + off, K ? mg->rgrad_v.as<float>() + off * K : nullptr, st);
-    ++tr->launches;
+  const uint8_t* in_rowv = mg->slab + L.off_in_rowv;
+  for (int s = 0; s < S; ++s) {
+    const uint32_t* slots_s = mg->slots.as<uint32_t>() + (size_t)s * cap;
+    const uint32_t* rows_s = reinterpret_cast<const uint32_t*>(mg->slab + off_rows_p) + (size_t)s * cap;
+    const uint8_t* rowv_s = in_rowv + (size_t)s * mg->max_rows * rowv_words * 4;
+    const uint32_t* meta_s = meta_p + (size_t)s * 4;
+    unsigned long long* uniq_s = reinterpret_cast<unsigned long long*>(mg->peers.slab[s] + L.off_uniq);
+    // every source sends about nnz / S tokens here; the kernels loop, so the bound only sizes the grid
+    const uint64_t work = (uint64_t)nnz / (uint64_t)S + 1024;
+    if (t->view.lazy) {
+      XF_TRY(t->next_seq());
+      xf_launch_push_tokens_lr(t->view, slots_s, rows_s, reinterpret_cast<const float*>(rowv_s), meta_s, cap, work, t->seq,
+                               t->d_rows_by_seq, uniq_s, st);
+      ++tr->launches;
+    } else {
+      xf_launch_acc_tokens(t->view, slots_s, rows_s, rowv_s, meta_s, cap, work, mg->touched.as<uint32_t>(), st);
+      xf_launch_update_touched_dev(t->view, mg->touched.as<uint32_t>(), work, meta_s, meta_s + 1, cap,
+                                   xf_acc_touched_extra(mg->K, work),
+                                   (s > 0 && mg->side_v.p) ? mg->side_v.as<float>() + (size_t)s * cap * (size_t)mg->K : nullptr,
+                                   uniq_s, st);
+      tr->launches += 2;
+    }
   }
   if (pm) XF_CUDA_TRY(cudaEventRecord(pm[3], st));
-  if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) {
-    cudaEventRecord(mg->tev[mg->tsteps * 11 + 10], st);
-    ++mg->tsteps;
-  }
-  tr->host_unique += n_send;  // statistics: unique keys of this rank's batch
+  XF_MG_MARK(6);
+  xf_launch_signal(mg->peers, L, S, me, XF_F_DONE, step, p, nullptr, 0, st);
+  ++tr->launches;
+  if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) { cudaEventRecord(mg->tev[mg->tsteps * XF_TR_NMARK + 7], st); ++mg->tsteps; }
   XF_CUDA_TRY(cudaGetLastError());
   return XF_OK;
 }

@@ -37,6 +37,43 @@ XF_DLL int xf_hash_decimal_ids_device(const uint32_t* d_ids, uint64_t n, uint64_
   return xf_launch_hash_ids(d_ids, (uint32_t)n, d_keys, (cudaStream_t)cuda_stream);
 }
 
+// Pre-population: what a Pull of the ids [first, first + n) by any worker leaves behind — their keys
+// exist in the table with default contents (store[key], ftrl.h:56 / sgd.h:48).  Sharded tables keep only
+// the keys of their own range (postoffice.cc:134-143).  Ids are hashed as their decimal strings.
+__global__ void xf_k_touch_ids(XfTableView t, uint64_t first, uint64_t n, uint64_t width, int S, int shard) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t v = first + i;
+    char rev[20];
+    int len = 0;
+    do { rev[len++] = (char)('0' + v % 10u); v /= 10u; } while (v);
+    char buf[20];
+    for (int j = 0; j < len; ++j) buf[j] = rev[len - 1 - j];
+    const uint64_t key = xf_murmur64a(buf, (uint64_t)len);
+    if (S > 1) {
+      const uint64_t q = key / width;
+      if ((int)(q < (uint64_t)S ? q : (uint64_t)S - 1) != shard) continue;
+    }
+    XfHead h;
+    xf_probe<true>(t, key, &h);
+  }
+}
+
+XF_DLL int xf_table_touch_decimal_ids(xf_table* t, uint64_t first_id, uint64_t count) {
+  if (!t) return XF_ERR_ARG;
+  XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
+  const int S = t->cfg.num_shards;
+  const uint64_t width = 0xFFFFFFFFFFFFFFFFull / (uint64_t)(S > 0 ? S : 1);
+  const uint64_t chunk = 1ull << 24;
+  for (uint64_t done = 0; done < count; done += chunk) {
+    const uint64_t n = count - done < chunk ? count - done : chunk;
+    XF_TRY(t->ensure_room(S > 1 ? n / (uint64_t)S + n / (8 * (uint64_t)S) + 65536 : n));
+    xf_k_touch_ids<<<xf_grid_for(n, 256, 8), 256, 0, t->stream>>>(t->view, first_id + done, n, width, S, t->cfg.shard_index);
+    ++t->launches;
+    XF_CUDA_TRY(cudaGetLastError());
+  }
+  return XF_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 // Text block -> CSR on the device: the parser half of
 // LoadData::load_minibatch_hash_data_fread (load_data_from_disk.cc:126-209).  The host still forms the

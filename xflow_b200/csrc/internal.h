@@ -69,7 +69,7 @@ struct xf_table {
   uint32_t seq = 0;
   uint32_t* d_rows_by_seq = nullptr;
   size_t rows_cap = 0;
-  int next_seq();            // advances seq, growing rows_by_seq when needed
+  int next_seq();            // advances seq; flushes all pending steps and restarts when the ring is used up
   // scratch for the host-pointer API (pull/push/import/export on host arrays); like KVWorker::Push/Pull
   // (kv_app.h:110-165) those entry points may be called from several threads: serialised by this mutex
   std::mutex host_mu;
@@ -101,12 +101,23 @@ struct xf_trainer {
   float* d_abs_loss = nullptr;          // 2 slots
   float* h_abs_loss = nullptr;          // pinned, 2 slots
   uint64_t n_steps = 0, n_rows = 0, n_nnz = 0;
-  uint64_t host_unique = 0;             // unique keys counted on the host (sharded path)
   uint32_t last_rows = 0;
   uint64_t launches = 0;
-  // device-side ingest (xf_trainer_ingest_text): raw text, parser scratch, the block's CSR
-  XfDevBuf ing_text, ing_scratch, ing_row_ptr, ing_keys, ing_labels, ing_totals;
-  XfPinBuf ing_stage;
+  // device-side ingest (xf_trainer_ingest_begin / _end): two sets of {raw text, the block's CSR}, so that
+  // block i+1 is copied and parsed on the ingest stream while block i is being trained on the table stream
+  struct IngestSet {
+    XfDevBuf text, row_ptr, keys, labels, totals;
+    XfPinBuf stage;                 // page-locked copy of a pageable source
+    uint32_t* h_totals = nullptr;   // pinned {rows, tokens, parse error}
+    cudaEvent_t parsed = nullptr;   // H2D + parse of this set finished (ingest stream)
+    cudaEvent_t consumed = nullptr; // the last step that reads this set finished (table stream)
+    uint32_t rows = 0, nnz = 0, max_rows = 0, max_tok = 0;
+  };
+  IngestSet ing[2];
+  XfDevBuf ing_scratch;
+  cudaStream_t ing_stream = nullptr;
+  int ing_cur = 0;                  // the set xf_trainer_step_ingested works on
+  bool ing_pending = false;         // xf_trainer_ingest_begin issued, _end not yet called
   uint32_t ing_rows = 0, ing_nnz = 0;
   void* mg = nullptr;                   // multi-GPU exchange state (comm.cu)
   cudaEvent_t input_ready = nullptr;    // set by the host-batch paths: H2D of the batch about to be stepped
@@ -127,5 +138,6 @@ int xf_mg_create(xf_trainer* tr);
 void xf_mg_destroy(xf_trainer* tr);
 int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys, const uint8_t* d_labels,
                uint32_t rows, uint32_t nnz, int mode, float* d_abs_loss, cudaEvent_t* prof_marks);
+int xf_mg_unique(xf_trainer* tr, unsigned long long* out);
 int xf_comm_nranks(xf_comm* c);
 int xf_comm_rank(xf_comm* c);

@@ -60,14 +60,28 @@ __device__ __forceinline__ void xf_stv(float* p, const float (&o)[VEC]) {
 //   SLOTG = true : gradients are the row's own accumulators (fused step).  g <- g / rows, then the
 //                  accumulators are reset (g = -0.0 marker, L = Aq = 0).
 //   SLOTG = false: gradients come from gw[i] / gv[i*K+k] (Push).  part bit0: apply w, bit1: apply v.
+// Sharded step (comm.cu): the list is the first *n_dev entries of `slots` plus `extra_n` entries at
+// slots[extra_base ...) (the accumulation kernel's cache flushes), and the divisor is *rows_dev — both
+// known only on the device (they arrive with the source rank's flag).  live_total may be peer memory.
+// v0_side (sources >= 1 of a round): the latent gradient is formed with the row as the source PULLED it,
+// v0_side[token * K ..], token = the entry's own position, or slots[extra_base + extra_n + j] for extra entry j
+// (earlier sources of the same round may have changed v since).
 template <int VEC, bool SLOTG>
 __global__ void __launch_bounds__(256)
 xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int tps, double rows,
             const float* __restrict__ gw, const float* __restrict__ gv, int part,
-            unsigned long long* __restrict__ live_total) {
+            unsigned long long* __restrict__ live_total, const uint32_t* __restrict__ n_dev,
+            const uint32_t* __restrict__ rows_dev, uint32_t extra_base, uint32_t extra_n,
+            const float* __restrict__ v0_side) {
   __shared__ unsigned int s_live;
   if (threadIdx.x == 0) s_live = 0;
   __syncthreads();
+  uint64_t n_head = n;  // entries [0, n_head) are slots[0, n_head); entries [n_head, n) are slots[extra_base, ...)
+  if (n_dev != nullptr) {
+    n_head = min((uint64_t)__ldg(n_dev), (uint64_t)extra_base);
+    n = n_head + extra_n;
+    rows = (double)__ldg(rows_dev);
+  }
   unsigned int live_acc = 0;
   const int K = t.K;
   const unsigned lane = threadIdx.x & 31u;
@@ -86,7 +100,8 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
     // evicted (LRU thrash: ncu showed 44 % L2 hits forward).
     const uint64_t e_fwd = base + lane;
     const uint64_t e_i = (SLOTG && e_fwd < n) ? (n - 1 - e_fwd) : e_fwd;
-    const uint32_t s_lane = (e_fwd < n) ? __ldcs(slots + e_i) : 0xFFFFFFFFu;
+    const uint64_t e_phys = (e_i < n_head) ? e_i : (uint64_t)extra_base + (e_i - n_head);
+    const uint32_t s_lane = (e_fwd < n) ? __ldcs(slots + e_phys) : 0xFFFFFFFFu;
     unsigned pend = __ballot_sync(0xffffffffu, s_lane != 0xFFFFFFFFu);
     // rows actually updated (= unique keys of the batch in the fused step)
     if (live_total != nullptr && lane == 0) live_acc += __popc(pend);
@@ -97,6 +112,7 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
       const unsigned src = (gi < cnt) ? __fns(pend, 0, gi + 1) : 0u;
       const uint32_t s = __shfl_sync(0xffffffffu, s_lane, (int)src);
       const uint64_t i = __shfl_sync(0xffffffffu, (unsigned long long)e_i, (int)src);
+      const uint64_t i_phys = __shfl_sync(0xffffffffu, (unsigned long long)e_phys, (int)src);
       uint8_t* rowp = (gi < cnt) ? xf_row(t, s) : nullptr;
       pend = (cnt <= ngroups) ? 0u : (pend & ~((2u << __fns(pend, 0, ngroups)) - 1u));
 
@@ -114,6 +130,14 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
       if (has0) {
         xf_ldv<VEC>(vp + q * VEC, v0);
         if (t.opt == XF_OPT_FTRL) { xf_ldv<VEC>(nvp + q * VEC, n0); xf_ldv<VEC>(zvp + q * VEC, z0); }
+      }
+      // sharded step, sources >= 1: the latent row as pulled (issued with the other loads)
+      float p0[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) p0[e] = 0.f;
+      if (SLOTG && v0_side != nullptr && has0) {
+        const uint64_t tok = (i_phys < (uint64_t)extra_base) ? i_phys : (uint64_t)__ldg(slots + i_phys + extra_n);
+        xf_ldv<VEC>(v0_side + tok * (uint64_t)K + q * VEC, p0);
       }
       // fused step: gv[k] = Aq - v[k] * L (table.cuh); every lane of the group reads the same 16 bytes
       double accL = 0.0, accA = 0.0;
@@ -157,8 +181,20 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
             for (int e = 0; e < VEC; ++e) { v[e] = xf_v_init(t, key, (uint32_t)(k + e)); nn[e] = 0.f; zz[e] = 0.f; }
           }
           if (SLOTG) {
+            float vp0[VEC];  // v the gradient is defined on: the pulled one if given, else the row's
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) g[e] = xf_div_rows((float)(accA - (double)v[e] * accL), rows);
+            for (int e = 0; e < VEC; ++e) vp0[e] = v[e];
+            if (v0_side != nullptr) {
+              if (c == q) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) vp0[e] = p0[e];
+              } else {
+                const uint64_t tok = (i_phys < (uint64_t)extra_base) ? i_phys : (uint64_t)__ldg(slots + i_phys + extra_n);
+                xf_ldv<VEC>(v0_side + tok * (uint64_t)K + k, vp0);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) g[e] = xf_div_rows((float)(accA - (double)vp0[e] * accL), rows);
           } else {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) g[e] = gv[i * (uint64_t)K + k + e];
@@ -185,7 +221,7 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
   if (live_total != nullptr) {
     if (lane == 0 && live_acc) atomicAdd(&s_live, live_acc);
     __syncthreads();
-    if (threadIdx.x == 0 && s_live) atomicAdd(live_total, (unsigned long long)s_live);
+    if (threadIdx.x == 0 && s_live) atomicAdd_system(live_total, (unsigned long long)s_live);
   }
 }
 
@@ -382,14 +418,42 @@ void xf_launch_fill(const XfTableView& t, cudaStream_t st) {
 template <bool SLOTG>
 static void xf_launch_update_t(const XfTableView& t, const uint32_t* slots, uint64_t n, double rows,
                                const float* gw, const float* gv, int part, unsigned long long* live_total,
-                               cudaStream_t st) {
+                               cudaStream_t st, const uint32_t* n_dev = nullptr, const uint32_t* rows_dev = nullptr,
+                               uint32_t extra_base = 0, uint32_t extra_n = 0, const float* v0_side = nullptr) {
   const int tps = xf_tps_for(t.K);
   const int grid = xf_grid_for(n * (uint64_t)tps, 256, 8);
+#define XF_UPD_ARGS t, slots, n, tps, rows, gw, gv, part, live_total, n_dev, rows_dev, extra_base, extra_n, v0_side
   switch (xf_vec_for(t.K)) {
-    case 4: xf_k_update<4, SLOTG><<<grid, 256, 0, st>>>(t, slots, n, tps, rows, gw, gv, part, live_total); break;
-    case 2: xf_k_update<2, SLOTG><<<grid, 256, 0, st>>>(t, slots, n, tps, rows, gw, gv, part, live_total); break;
-    default: xf_k_update<1, SLOTG><<<grid, 256, 0, st>>>(t, slots, n, tps, rows, gw, gv, part, live_total); break;
+    case 4: xf_k_update<4, SLOTG><<<grid, 256, 0, st>>>(XF_UPD_ARGS); break;
+    case 2: xf_k_update<2, SLOTG><<<grid, 256, 0, st>>>(XF_UPD_ARGS); break;
+    default: xf_k_update<1, SLOTG><<<grid, 256, 0, st>>>(XF_UPD_ARGS); break;
   }
+#undef XF_UPD_ARGS
+}
+
+// sharded step: touched[] of one source rank, list length and divisor read on the device
+void xf_launch_update_touched_dev(const XfTableView& t, const uint32_t* touched, uint64_t work_bound,
+                                  const uint32_t* n_dev, const uint32_t* rows_dev, uint32_t extra_base,
+                                  uint32_t extra_n, const float* v0_side, unsigned long long* unique_total,
+                                  cudaStream_t st) {
+  xf_launch_update_t<true>(t, touched, work_bound + extra_n, 1.0, nullptr, nullptr, 3, unique_total, st, n_dev, rows_dev,
+                           extra_base, extra_n, v0_side);
+}
+
+// lazy tables: fold every pending optimizer step into its row (tags back to 0); lets the batch sequence
+// numbers restart, so rows_by_seq is a fixed-size ring instead of an ever-growing array
+__global__ void xf_k_flush_pending(XfTableView t) {
+  const uint64_t cap = t.mask + 1;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < cap; r += (uint64_t)gridDim.x * blockDim.x) {
+    uint8_t* rowp = xf_row(t, r);
+    XfHead h = xf_load_head(rowp);
+    if (h.key == XF_EMPTY_KEY || !xf_has_pending(t, h)) continue;
+    xf_apply_pending(t, h);
+    xf_store_head(rowp, h);
+  }
+}
+void xf_launch_flush_pending(const XfTableView& t, cudaStream_t st) {
+  xf_k_flush_pending<<<xf_grid_for(t.mask + 1, 256, 8), 256, 0, st>>>(t);
 }
 
 void xf_launch_update_touched(const XfTableView& t, const uint32_t* touched, uint64_t nnz, double rows,

@@ -44,8 +44,13 @@ XF_DLL int xf_hash_decimal_ids(const uint64_t* ids, uint64_t n, uint64_t* out) {
 
 struct xf_loader {
   FILE* fp = nullptr;
-  uint64_t file_size = 0, file_pos = 0;  // reads go through pread on fileno(fp)
-  char* buf = nullptr;
+  uint64_t file_size = 0, file_pos = 0;  // regular files: reads go through pread on fileno(fp)
+  bool regular = true;                   // FIFOs / pipes / stdin are read sequentially until EOF
+  // two raw-text buffers, alternated by every block: the text of block i stays valid (e.g. as the source
+  // of an asynchronous H2D copy, xf_trainer_ingest_begin) while block i+1 is being read
+  char* buf = nullptr;                   // the current one
+  char* buf_set[2] = {nullptr, nullptr};
+  int buf_cur = 0;
   bool buf_pinned = false;
   size_t buf_size = 0, bmax = 0, btop = 0;
   // two output sets, alternated by every xf_loader_next: the arrays of block i stay valid (e.g. as
@@ -88,32 +93,32 @@ XF_DLL int xf_loader_open(xf_loader** out, const char* path, uint64_t block_byte
   l->fp = fp;
   {
     struct stat sb;
-    l->file_size = (fstat(fileno(fp), &sb) == 0) ? (uint64_t)sb.st_size : 0;
+    const bool ok = fstat(fileno(fp), &sb) == 0;
+    l->regular = ok && S_ISREG(sb.st_mode);
+    l->file_size = (ok && l->regular) ? (uint64_t)sb.st_size : 0;
   }
   l->buf_size = (size_t)block_bytes;
   {
     bool pin_text = true;  // the raw block is also what the device parser uploads (xf_loader_next_raw)
-    l->buf = (char*)xf_host_alloc(l->buf_size + 1, &pin_text);
+    l->buf_set[0] = (char*)xf_host_alloc(l->buf_size + 1, &pin_text);
+    bool pin2 = pin_text;
+    l->buf_set[1] = (char*)xf_host_alloc(l->buf_size + 1, &pin2);
+    if (pin2 != pin_text && l->buf_set[1]) {  // keep both buffers of one kind
+      xf_host_free(l->buf_set[1], pin2);
+      l->buf_set[1] = nullptr;
+    }
     l->buf_pinned = pin_text;
+    l->buf = l->buf_set[0];
   }
-  // shortest legal row "0\ta:b:c\n" = 8 bytes, shortest extra token " a:b:c" = 6 bytes
+  // shortest row "0\n" = 2 bytes, shortest token "a:b:c " ~ 4 bytes.  The CSR output sets of the HOST parser
+  // are allocated by the first xf_loader_next: callers that only form raw blocks (device parser) never pay
+  // for them.
   l->max_rows = l->buf_size / 2 + 2;
   l->max_tok = l->buf_size / 4 + 2;
-  int ndev = 0;
-  bool pin = (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0);
-  if (!pin) cudaGetLastError();
-  l->pinned = pin;
-  for (int s = 0; s < 2; ++s) {
-    bool p1 = l->pinned, p2 = l->pinned, p3 = l->pinned;
-    l->row_ptr_set[s] = (uint32_t*)xf_host_alloc((l->max_rows + 1) * 4, &p1);
-    l->keys_set[s] = (uint64_t*)xf_host_alloc(l->max_tok * 8, &p2);
-    l->labels_set[s] = (uint8_t*)xf_host_alloc(l->max_rows, &p3);
-    if (!l->buf || !l->row_ptr_set[s] || !l->keys_set[s] || !l->labels_set[s] || !(p1 == p2 && p2 == p3) ||
-        (s == 1 && p1 != l->pinned)) {
-      xf_set_error("loader allocation failed");
-      return XF_ERR_IO;
-    }
-    l->pinned = p1;
+  if (!l->buf_set[0] || !l->buf_set[1]) {
+    xf_set_error("loader allocation failed");
+    xf_loader_close(l);
+    return XF_ERR_IO;
   }
   *out = l;
   return XF_OK;
@@ -122,7 +127,8 @@ XF_DLL int xf_loader_open(xf_loader** out, const char* path, uint64_t block_byte
 XF_DLL int xf_loader_close(xf_loader* l) {
   if (!l) return XF_OK;
   if (l->fp) fclose(l->fp);
-  xf_host_free(l->buf, l->buf_pinned);
+  xf_host_free(l->buf_set[0], l->buf_pinned);
+  xf_host_free(l->buf_set[1], l->buf_pinned);
   for (int s = 0; s < 2; ++s) {
     xf_host_free(l->row_ptr_set[s], l->pinned);
     xf_host_free(l->keys_set[s], l->pinned);
@@ -136,6 +142,17 @@ XF_DLL int xf_loader_close(xf_loader* l) {
 // split across a few threads (pread at disjoint offsets): one core copies out of the page cache at
 // ~4 GB/s, which would otherwise cap file -> device throughput now that parsing runs on the GPU.
 static size_t xf_read_block(xf_loader* l, char* dst, size_t n) {
+  if (!l->regular) {
+    // not seekable (FIFO, pipe, /dev/stdin): plain sequential reads until the buffer is full or EOF, like
+    // the reference's fread (load_data_from_disk.cc:112)
+    size_t done = 0;
+    while (done < n) {
+      const size_t r = fread(dst + done, 1, n - done, l->fp);
+      if (r == 0) break;
+      done += r;
+    }
+    return done;
+  }
   const int fd = fileno(l->fp);
   const uint64_t remaining = l->file_size > l->file_pos ? l->file_size - l->file_pos : 0;
   if (n > remaining) n = (size_t)remaining;
@@ -172,8 +189,11 @@ static size_t xf_read_block(xf_loader* l, char* dst, size_t n) {
 
 // block formation (load_data_from_disk.cc:108-124): returns the length of the parse region [0, end)
 static size_t xf_loader_form_block(xf_loader* l) {
-  char* buf = l->buf;
-  if (l->bmax < l->btop) memmove(buf, buf + l->bmax, l->btop - l->bmax);
+  // the tail carried over from the previous block moves to the front of the OTHER buffer
+  char* prev = l->buf;
+  l->buf_cur ^= 1;
+  char* buf = l->buf = l->buf_set[l->buf_cur];
+  if (l->bmax < l->btop) memcpy(buf, prev + l->bmax, l->btop - l->bmax);
   l->btop -= l->bmax;
   l->btop += xf_read_block(l, buf + l->btop, l->buf_size - 1 - l->btop);
   l->bmax = l->btop;
@@ -197,14 +217,45 @@ XF_DLL int xf_loader_next_raw(xf_loader* l, const char** text, uint64_t* len) {
   return XF_OK;
 }
 
+static int xf_loader_alloc_sets(xf_loader* l) {
+  if (l->row_ptr_set[0]) return XF_OK;
+  int ndev = 0;
+  bool pin = (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0);
+  if (!pin) cudaGetLastError();
+  l->pinned = pin;
+  for (int s = 0; s < 2; ++s) {
+    bool p1 = l->pinned, p2 = l->pinned, p3 = l->pinned;
+    l->row_ptr_set[s] = (uint32_t*)xf_host_alloc((l->max_rows + 1) * 4, &p1);
+    l->keys_set[s] = (uint64_t*)xf_host_alloc(l->max_tok * 8, &p2);
+    l->labels_set[s] = (uint8_t*)xf_host_alloc(l->max_rows, &p3);
+    if (!l->row_ptr_set[s] || !l->keys_set[s] || !l->labels_set[s] || !(p1 == p2 && p2 == p3) || (s == 1 && p1 != l->pinned)) {
+      xf_set_error("loader allocation failed");
+      return XF_ERR_IO;
+    }
+    l->pinned = p1;
+  }
+  return XF_OK;
+}
+
+// back to the first byte of the file (regular files only): the next block is the first block again.  Lets a
+// caller run every epoch on one loader instead of re-allocating page-locked buffers per epoch.
+XF_DLL int xf_loader_rewind(xf_loader* l) {
+  if (!l) return XF_ERR_ARG;
+  if (!l->regular) { xf_set_error("loader: cannot rewind a stream"); return XF_ERR_IO; }
+  l->file_pos = 0;
+  l->bmax = l->btop = 0;
+  return XF_OK;
+}
+
 XF_DLL int xf_loader_next(xf_loader* l, uint32_t* rows_out, uint32_t* nnz_out) {
   if (!l || !rows_out || !nnz_out) return XF_ERR_ARG;
-  char* buf = l->buf;
+  if (xf_loader_alloc_sets(l) != XF_OK) return XF_ERR_IO;
   l->cur ^= 1;
   l->row_ptr = l->row_ptr_set[l->cur];
   l->keys = l->keys_set[l->cur];
   l->labels = l->labels_set[l->cur];
   const size_t end = xf_loader_form_block(l);
+  char* buf = l->buf;
 
   // --- parse
   uint32_t rows = 0, nnz = 0;

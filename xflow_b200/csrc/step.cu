@@ -22,7 +22,6 @@
 
 #include "kernels.h"
 #include "table.cuh"
-#include "workset.cuh"
 
 #define XF_NO_SLOT 0xFFFFFFFFu
 #define XF_CACHED_CHUNKS 2  // 64-token chunks whose slots stay in registers (rows <= 128 tokens)
@@ -249,154 +248,6 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
   }
 }
 
-// -------------------------------------------------------------------------------------------------
-// The same step against a per-batch WORK SET (sharded / multi-GPU worker, workset.cuh): parameters
-// were pulled into compact arrays, gradients accumulate into compact arrays.  Identical arithmetic.
-// -------------------------------------------------------------------------------------------------
-template <bool FM, int VEC>
-__global__ void __launch_bounds__(256)
-xf_k_step_ws(XfWorkSet ws, const uint32_t* __restrict__ row_ptr, const uint64_t* __restrict__ keys,
-             const uint8_t* __restrict__ labels, int B, int mode, float* __restrict__ loss_out,
-             float* __restrict__ pctr_out, float* __restrict__ abs_loss_sum, int log2nc) {
-  __shared__ float s_abs[8];
-  extern __shared__ __align__(16) unsigned char xf_smem[];
-  float abs_acc = 0.f;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * warps_per_block;
-  const int K = ws.K;
-  // CTA hot-key cache, as in xf_k_step: double acc[NC][3] = {G, L, Aq} | uint32 tag[NC] (tag = u)
-  const int NC = (FM && log2nc >= 0 && mode == 0) ? (1 << log2nc) : 0;
-  double* c_acc = reinterpret_cast<double*>(xf_smem);
-  uint32_t* c_tag = reinterpret_cast<uint32_t*>(xf_smem + (size_t)NC * 24);
-  if (NC) {
-    for (int e = threadIdx.x; e < NC; e += blockDim.x) c_tag[e] = XF_NO_SLOT;
-    for (int e = threadIdx.x; e < NC * 3; e += blockDim.x) c_acc[e] = 0.0;
-    __syncthreads();
-  }
-
-  for (int row = gwarp; row < B; row += nwarps) {
-    const uint32_t beg = __ldg(row_ptr + row);
-    const uint32_t end = __ldg(row_ptr + row + 1);
-    const int chunks = (int)((end - beg + 63u) >> 6);
-    float wsum = 0.f, ssum = 0.f, qsum = 0.f;
-    uint32_t u_c[2 * XF_CACHED_CHUNKS];
-#pragma unroll
-    for (int c = 0; c < 2 * XF_CACHED_CHUNKS; ++c) u_c[c] = XF_NO_SLOT;
-
-    for (int ch = 0; ch < chunks; ++ch) {
-      const uint32_t j0 = beg + (uint32_t)ch * 64u + (uint32_t)lane;
-      const uint32_t j1 = j0 + 32u;
-      const uint64_t k0 = j0 < end ? __ldcs(keys + j0) : 0ull;
-      const uint64_t k1 = j1 < end ? __ldcs(keys + j1) : 0ull;
-      const uint32_t u0 = j0 < end ? xf_ws_find(ws, k0) : XF_NO_SLOT;
-      const uint32_t u1 = j1 < end ? xf_ws_find(ws, k1) : XF_NO_SLOT;
-      if (u0 != XF_NO_SLOT) wsum += __ldca(ws.w + u0);  // read-only here: L1 keeps the hot keys SM-local
-      if (u1 != XF_NO_SLOT) wsum += __ldca(ws.w + u1);
-      if (FM) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t u = h ? u1 : u0;
-          if (u == XF_NO_SLOT) continue;
-          const float* vp = ws.v + (uint64_t)u * K;
-          float st = 0.f, qt = 0.f;
-          for (int k = 0; k < K; k += VEC) {
-            float v[VEC];
-            xf_ldv_step<VEC>(vp + k, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) { st += v[e]; qt = __fadd_rn(qt, __fmul_rn(v[e], v[e])); }
-          }
-          ssum += st;
-          qsum += qt;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < XF_CACHED_CHUNKS; ++c)
-        if (ch == c) { u_c[2 * c] = u0; u_c[2 * c + 1] = u1; }
-    }
-
-    const float wx = xf_warp_sum(wsum);
-    float S = 0.f, arg = wx;
-    if (FM) {
-      S = xf_warp_sum(ssum);
-      const float Q = xf_warp_sum(qsum);
-      arg = __fadd_rn(wx, __fsub_rn(__fmul_rn(S, S), Q));
-    }
-    const float pctr = xf_sigmoid(arg);
-    if (mode == 1) {
-      if (lane == 0 && pctr_out) pctr_out[row] = pctr;
-      continue;
-    }
-    const float loss = __fsub_rn(pctr, (float)labels[row]);
-    if (lane == 0 && loss_out) loss_out[row] = loss;
-    abs_acc += fabsf(loss);
-
-    float gw_c = loss;
-    if (FM) {
-      gw_c = 0.f;
-      for (int k = 0; k < K; ++k) gw_c += loss;
-    }
-    const double gw_d = (double)gw_c;
-    for (int ch = 0; ch < chunks; ++ch) {
-      const uint32_t j0 = beg + (uint32_t)ch * 64u + (uint32_t)lane;
-      const uint32_t j1 = j0 + 32u;
-      uint32_t u0 = XF_NO_SLOT, u1 = XF_NO_SLOT;
-      if (ch < XF_CACHED_CHUNKS) {
-#pragma unroll
-        for (int c = 0; c < XF_CACHED_CHUNKS; ++c)
-          if (ch == c) { u0 = u_c[2 * c]; u1 = u_c[2 * c + 1]; }
-      } else {
-        if (j0 < end) u0 = xf_ws_find(ws, __ldg(keys + j0));
-        if (j1 < end) u1 = xf_ws_find(ws, __ldg(keys + j1));
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t u = h ? u1 : u0;
-        // same-key tokens of the row are merged: the group's lowest lane adds count x term
-        const unsigned grp = __match_any_sync(0xffffffffu, (u != XF_NO_SLOT) ? u : (0xFFFFFF00u | (uint32_t)lane));
-        if (u == XF_NO_SLOT || lane != __ffs(grp) - 1) continue;
-        const double cnt = (double)__popc(grp);
-        const double gd = gw_d * cnt, ld = (double)loss * cnt, ad = (double)loss * (double)S * cnt;  // exact products
-        bool cached = false;
-        if (NC) {
-          const uint32_t e = (u * 2654435761u) >> (32 - log2nc);
-          const uint32_t prev = atomicCAS(c_tag + e, XF_NO_SLOT, u);
-          if (prev == XF_NO_SLOT || prev == u) {
-            cached = true;
-            atomicAdd(c_acc + 3 * e, gd);
-            atomicAdd(c_acc + 3 * e + 1, ld);
-            atomicAdd(c_acc + 3 * e + 2, ad);
-          }
-        }
-        if (!cached) {
-          atomicAdd(ws.gw + u, gd);
-          if (FM) { atomicAdd(ws.acc + 2 * (uint64_t)u, ld); atomicAdd(ws.acc + 2 * (uint64_t)u + 1, ad); }
-        }
-      }
-    }
-  }
-  if (NC) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < NC; e += blockDim.x) {
-      const uint32_t u = c_tag[e];
-      if (u == XF_NO_SLOT) continue;
-      atomicAdd(ws.gw + u, c_acc[3 * e]);
-      atomicAdd(ws.acc + 2 * (uint64_t)u, c_acc[3 * e + 1]);
-      atomicAdd(ws.acc + 2 * (uint64_t)u + 1, c_acc[3 * e + 2]);
-    }
-  }
-  if (abs_loss_sum != nullptr && mode == 0) {
-    if (lane == 0) s_abs[threadIdx.x >> 5] = abs_acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_abs[w];
-      atomicAdd(abs_loss_sum, tot);
-    }
-  }
-}
-
 int xf_sms();
 int xf_grid_for(uint64_t work_items, int block, int blocks_per_sm);
 
@@ -438,24 +289,3 @@ void xf_launch_step(const XfTableView& t, const uint32_t* row_ptr, const uint64_
   }
 #undef XF_STEP_ARGS
 }
-
-void xf_launch_step_ws(const XfWorkSet& ws, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* labels,
-                       int B, int mode, float* loss_out, float* pctr_out, float* abs_loss_sum, cudaStream_t st) {
-  if (B <= 0) return;
-  const int block = 256;
-  const int grid = xf_grid_for((uint64_t)B * 32, block, 8);
-  const int lg = xf_step_cache_log2(ws.K);
-  const size_t smem = lg >= 0 ? ((size_t)1 << lg) * 28 : 0;
-#define XF_WS_ARGS ws, row_ptr, keys, labels, B, mode, loss_out, pctr_out, abs_loss_sum, lg
-  if (ws.K == 0) {
-    xf_k_step_ws<false, 1><<<grid, block, 0, st>>>(XF_WS_ARGS);
-  } else {
-    switch (xf_vec_for(ws.K)) {
-      case 4: xf_k_step_ws<true, 4><<<grid, block, smem, st>>>(XF_WS_ARGS); break;
-      case 2: xf_k_step_ws<true, 2><<<grid, block, smem, st>>>(XF_WS_ARGS); break;
-      default: xf_k_step_ws<true, 1><<<grid, block, smem, st>>>(XF_WS_ARGS); break;
-    }
-  }
-#undef XF_WS_ARGS
-}
-
