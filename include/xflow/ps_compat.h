@@ -190,9 +190,14 @@ struct TableHandle {
     xf_table* t = resolve();
     const uint64_t n = req.keys.size();
     ps::KVPairs<float> res;
+    // the row width is the TABLE's latent dimension (a Server(opt, K) or a caller-supplied table need not
+    // agree with the global xflow::v_dim), never a guess: both directions are sized and checked with it
+    int K = 0;
+    if (xf_table_latent_dim(t, &K) != XF_OK) throw std::runtime_error(std::string("xf_table_latent_dim: ") + xf_last_error());
+    if (latent && K <= 0) throw std::runtime_error("xflow handle: the latent (app 1) handle needs a table with latent_dim > 0");
+    const uint64_t dim = latent ? (uint64_t)K : 1u;
     if (meta.push) {
       // ftrl.h:54-79 / 112-146, sgd.h:46-59 / 90-103: one optimizer step per key with the pushed gradient
-      const uint64_t dim = latent ? (uint64_t)v_dim : 1u;
       if (req.vals.size() != n * dim) throw std::runtime_error("xflow handle: Push of " + std::to_string(req.vals.size()) +
                                                                 " values for " + std::to_string(n) + " keys");
       const int rc = latent ? xf_table_push(t, req.keys.data(), n, nullptr, req.vals.data())
@@ -201,7 +206,7 @@ struct TableHandle {
     } else {
       // ftrl.h:75-77 / 142-144: res.keys = req.keys, res.vals = keys x dim (missing keys are inserted)
       res.keys = req.keys;
-      res.vals.resize(n * (latent ? (uint64_t)v_dim : 1u));
+      res.vals.resize(n * dim);
       const int rc = latent ? xf_table_pull(t, req.keys.data(), n, nullptr, res.vals.data())
                             : xf_table_pull(t, req.keys.data(), n, res.vals.data(), nullptr);
       if (rc != XF_OK) throw std::runtime_error(std::string("xf_table_pull: ") + xf_last_error());

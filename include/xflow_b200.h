@@ -108,6 +108,7 @@ XF_DLL int xf_table_export(xf_table* t, const uint64_t* keys, uint64_t n, float*
 XF_DLL int xf_table_size(xf_table* t, uint64_t* n_keys);        /* = store.size() */
 XF_DLL int xf_table_capacity(xf_table* t, uint64_t* n_slots);
 XF_DLL int xf_table_row_bytes(xf_table* t, uint32_t* bytes);
+XF_DLL int xf_table_latent_dim(xf_table* t, int* latent_dim);   /* K of the table (0 = LR) */
 /* make room for at least n_keys keys at load factor <= 0.5 (rehashes on device if needed) */
 XF_DLL int xf_table_reserve(xf_table* t, uint64_t n_keys);
 /* Pre-populate: make the keys of the integer feature ids [first_id, first_id + count) exist with default

@@ -61,6 +61,48 @@ def test_golden_files_parse_like_the_host_loader(trainer, path, block_bytes):
     _same_blocks(host, _blocks_device(path, block_bytes, trainer))
 
 
+@pytest.mark.parametrize("path", [TRAIN, TEST])
+@pytest.mark.parametrize("block_bytes", [4096, 65536, 2 << 20])
+def test_golden_files_parse_like_the_reference_loader(trainer, path, block_bytes):
+    """The device parser DIRECTLY against the oracle's restatement of LoadData::load_minibatch_hash_data_fread
+    (which tests/test_oracle.py pins to the compiled reference): same blocks, rows, labels and std::hash keys —
+    not only transitively through this repo's own host parser."""
+    from oracle import oracle as O
+    ref = [(rp.astype(np.uint32), k, y.astype(np.uint8)) for rp, k, y in O.load_blocks(path, block_bytes)]
+    assert ref, "fixture missing"
+    _same_blocks(ref, _blocks_device(path, block_bytes, trainer))
+
+
+def test_two_phase_ingest_pipeline_equals_one_shot(trainer, tmp_path):
+    """xf_trainer_ingest_begin / _end with a block in flight while the previous one is exported and trained on:
+    the same CSR as the synchronous call, block after block (two device-side block buffers alternate)."""
+    import ctypes as C
+    row_ptr, ids, labels = datagen.make_ids(5, 6000, 20, 1 << 30, ragged=True)
+    path = str(tmp_path / "pipe-00000")
+    datagen.write_text(path, row_ptr, ids, labels)
+    want = _blocks_device(path, 1 << 16, trainer)
+    assert len(want) > 6
+    lib = api.lib()
+    ld = api.Loader(path, 1 << 16)
+    text, ln, r, z = C.c_void_p(), C.c_uint64(), C.c_uint32(), C.c_uint32()
+    assert lib.xf_loader_next_raw(ld.h, C.byref(text), C.byref(ln)) == 0
+    assert lib.xf_trainer_ingest_begin(trainer.h, text, ln.value) == 0
+    assert lib.xf_trainer_ingest_begin(trainer.h, text, ln.value) != 0      # one block in flight at most
+    got = []
+    while True:
+        nt, nl = C.c_void_p(), C.c_uint64()
+        assert lib.xf_loader_next_raw(ld.h, C.byref(nt), C.byref(nl)) == 0   # the other text buffer
+        assert lib.xf_trainer_ingest_end(trainer.h, C.byref(r), C.byref(z)) == 0, lib.xf_last_error()
+        trainer.step_ingested(0, r.value)                                    # asynchronous
+        if nl.value:
+            assert lib.xf_trainer_ingest_begin(trainer.h, nt, nl.value) == 0, lib.xf_last_error()
+        got.append(trainer.ingested_export(r.value, z.value))               # the CURRENT block, while the next parses
+        if not nl.value:
+            break
+    assert lib.xf_trainer_ingest_end(trainer.h, C.byref(r), C.byref(z)) != 0  # nothing in flight
+    _same_blocks(want, got)
+
+
 def test_synthetic_ragged_multi_block(trainer, tmp_path):
     row_ptr, ids, labels = datagen.make_ids(11, 20000, 24, 1 << 40, dist="zipf", ragged=True)
     path = str(tmp_path / "syn-00000")

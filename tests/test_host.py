@@ -218,6 +218,37 @@ def test_raw_blocks_are_the_parsed_blocks(block_bytes):
     assert b"".join(r.rstrip(b"\n") for r in raw).replace(b"\n", b"") == whole.replace(b"\n", b"")
 
 
+def test_loader_rewind_and_streams(tmp_path):
+    """One loader serves every epoch (xf_loader_rewind = re-opening the file, lr_worker.cc:184), and a FIFO —
+    which reports size 0 to fstat — is read sequentially to EOF like the reference's fread does."""
+    import threading
+    path = os.path.join(GOLDEN, "data", "small_train-00000")
+    first = [tuple(a.copy() for a in blk) for blk in api.Loader(path, 8192)]
+    ld = api.Loader(path, 8192)
+    again = []
+    for _ in range(2):
+        again.append([tuple(a.copy() for a in blk) for blk in ld])
+        assert api.lib().xf_loader_rewind(ld.h) == 0
+    for run in again:
+        assert len(run) == len(first)
+        for a, b in zip(run, first):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    fifo = str(tmp_path / "pipe-00000")
+    os.mkfifo(fifo)
+    data = open(path, "rb").read()
+
+    def feed():
+        with open(fifo, "wb") as f:
+            f.write(data)
+    th = threading.Thread(target=feed)
+    th.start()
+    got = [tuple(a.copy() for a in blk) for blk in api.Loader(fifo, 8192)]
+    th.join()
+    assert len(got) == len(first)
+    for a, b in zip(got, first):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_loader_fuzz_against_python_parser(tmp_path):
     """Random well-formed shards (random labels incl. floats, 0..6 tokens per row, fids of random bytes and
     lengths, CRLF or LF, with / without final newline) cut at random block sizes: the rows, labels and

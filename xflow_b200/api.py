@@ -52,6 +52,7 @@ SIGNATURES = {
     "xf_table_size": (_i, [_vp, _vp]),
     "xf_table_capacity": (_i, [_vp, _vp]),
     "xf_table_row_bytes": (_i, [_vp, _vp]),
+    "xf_table_latent_dim": (_i, [_vp, _vp]),
     "xf_table_reserve": (_i, [_vp, _u64]),
     "xf_table_list_keys": (_i, [_vp, _vp, _u64, _vp]),
     "xf_table_touch_decimal_ids": (_i, [_vp, _u64, _u64]),

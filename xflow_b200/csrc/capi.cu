@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 
 #include "internal.h"
 
@@ -105,6 +106,14 @@ int xf_table::alloc_table(uint64_t capacity) {
   while ((1ull << lg) < capacity) ++lg;
   view.log2cap = lg;
   view.stride = stride;
+  // probing buckets = the rows that share one 128-byte line (table.cuh: xf_probe_slot); XFLOW_BUCKET_LOG2
+  // overrides (0 = plain linear probing) for A/B measurements
+  uint32_t bs = 0;
+  while ((stride << (bs + 1)) <= 128u) ++bs;
+  const char* be = getenv("XFLOW_BUCKET_LOG2");
+  if (be && *be) bs = (uint32_t)std::min(std::max(atoi(be), 0), 4);
+  if (bs + 4 > lg) bs = 0;
+  view.bshift = bs;
   xf_launch_fill(view, stream);
   ++launches;
   XF_CUDA_TRY(cudaGetLastError());
@@ -128,8 +137,9 @@ int xf_table::check_error() {
 
 int xf_table::grow(uint64_t new_capacity) {
   XfTableView old = view;
-  XF_CUDA_TRY(cudaMemsetAsync(d_size, 0, sizeof(unsigned long long), stream));
-  XF_TRY(alloc_table(new_capacity));
+  const int rc = alloc_table(new_capacity);  // on failure the old table (and its size counter) stay as they are
+  if (rc != XF_OK) { view = old; return rc; }
+  XF_CUDA_TRY(cudaMemsetAsync(d_size, 0, sizeof(unsigned long long), stream));  // the rehash re-counts every key
   xf_launch_rehash(old, view, stream);
   ++launches;
   XF_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -199,10 +209,15 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
     return XF_ERR_ARG;
   }
   XF_CUDA_TRY(cudaSetDevice(cfg->device));
-  // The table is read and written one random 32-byte sector at a time.  The default L2 fetch
-  // granularity (64 B) doubles the DRAM traffic of every miss; ask for sector-sized fetches.
-  // (A hint: the driver may ignore it; measured with ncu dram__bytes_read.)
-  if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32) != cudaSuccess) cudaGetLastError();
+  // L2 fetch granularity = one probing bucket (LR: 4 rows = 128 B, so that the further probes of a bucket
+  // hit the line the first probe fetched; FM: head + latent row of a key are contiguous, 96+ B).  A hint —
+  // the driver may ignore it; measured with ncu dram__bytes_read.  XFLOW_L2_FETCH = 32 / 64 / 128 overrides.
+  {
+    int fetch = 128;
+    const char* fe = getenv("XFLOW_L2_FETCH");
+    if (fe && (atoi(fe) == 32 || atoi(fe) == 64 || atoi(fe) == 128)) fetch = atoi(fe);
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch) != cudaSuccess) cudaGetLastError();
+  }
   xf_table* t = new xf_table;
   t->cfg = *cfg;
   memset(&t->view, 0, sizeof(t->view));
@@ -299,6 +314,11 @@ XF_DLL int xf_table_capacity(xf_table* t, uint64_t* n_slots) {
 XF_DLL int xf_table_row_bytes(xf_table* t, uint32_t* bytes) {
   if (!t || !bytes) return XF_ERR_ARG;
   *bytes = t->view.stride;
+  return XF_OK;
+}
+XF_DLL int xf_table_latent_dim(xf_table* t, int* latent_dim) {
+  if (!t || !latent_dim) return XF_ERR_ARG;
+  *latent_dim = t->view.K;
   return XF_OK;
 }
 XF_DLL int xf_table_reserve(xf_table* t, uint64_t n_keys) {
@@ -480,18 +500,26 @@ XF_DLL int xf_table_save(xf_table* t, const char* path) {
   std::vector<uint8_t> present(n);
   XF_TRY(xf_table_export(t, keys.data(), n, w.data(), nw.data(), zw.data(), K ? v.data() : nullptr,
                          K ? nv.data() : nullptr, K ? zv.data() : nullptr, present.data()));
-  FILE* f = fopen(path, "wb");
-  if (!f) { xf_set_error("cannot open %s for writing", path); return XF_ERR_IO; }
+  // written under a temporary name and renamed: a reader never sees a half-written checkpoint, and a
+  // short write (ENOSPC ...) is an error, not a silently truncated file
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) { xf_set_error("cannot open %s for writing", tmp.c_str()); return XF_ERR_IO; }
   uint32_t K32 = (uint32_t)K;
-  fwrite("XFTB", 1, 4, f);
-  fwrite(&n, 8, 1, f); fwrite(&K32, 4, 1, f); fwrite(&has_nz, 4, 1, f);
-  fwrite(keys.data(), 8, n, f);
-  fwrite(w.data(), 4, n, f);
-  if (has_nz) { fwrite(nw.data(), 4, n, f); fwrite(zw.data(), 4, n, f); }
-  fwrite(v.data(), 4, n * K, f);
-  if (has_nz) { fwrite(nv.data(), 4, n * K, f); fwrite(zv.data(), 4, n * K, f); }
-  fwrite(present.data(), 1, n, f);
-  fclose(f);
+  bool ok = fwrite("XFTB", 1, 4, f) == 4 && fwrite(&n, 8, 1, f) == 1 && fwrite(&K32, 4, 1, f) == 1 && fwrite(&has_nz, 4, 1, f) == 1;
+  auto put = [&](const void* p, size_t sz, size_t cnt) { if (ok && cnt) ok = fwrite(p, sz, cnt, f) == cnt; };
+  put(keys.data(), 8, n);
+  put(w.data(), 4, n);
+  if (has_nz) { put(nw.data(), 4, n); put(zw.data(), 4, n); }
+  put(v.data(), 4, n * K);
+  if (has_nz) { put(nv.data(), 4, n * K); put(zv.data(), 4, n * K); }
+  put(present.data(), 1, n);
+  if (fclose(f) != 0) ok = false;
+  if (!ok || rename(tmp.c_str(), path) != 0) {
+    remove(tmp.c_str());
+    xf_set_error("write to %s failed", path);
+    return XF_ERR_IO;
+  }
   return XF_OK;
 }
 
@@ -545,8 +573,28 @@ XF_DLL int xf_table_load(xf_table* t, const char* path) {
     return XF_ERR_IO;
   }
   const size_t K = K32;
-  std::vector<uint64_t> keys(n);
-  std::vector<float> w(n), nw(n), zw(n), v(n * K), nv(n * K), zv(n * K);
+  // the header's key count must agree with the file's size before anything is allocated from it
+  {
+    const long here = ftell(f);
+    fseek(f, 0, SEEK_END);
+    const long fsz = ftell(f);
+    fseek(f, here, SEEK_SET);
+    const unsigned long long per = 8ull + 4ull * (has_nz ? 3 : 1) + 4ull * K * (has_nz ? 3 : 1) + 1ull;
+    if (here < 0 || fsz < here || n > (unsigned long long)(fsz - here) / per || (unsigned long long)(fsz - here) != n * per) {
+      fclose(f);
+      xf_set_error("corrupt or truncated checkpoint %s (%llu keys announced, %ld bytes of payload)", path, (unsigned long long)n, fsz - here);
+      return XF_ERR_IO;
+    }
+  }
+  std::vector<uint64_t> keys;
+  std::vector<float> w, nw, zw, v, nv, zv;
+  try {
+    keys.resize(n); w.resize(n); nw.resize(n); zw.resize(n); v.resize(n * K); nv.resize(n * K); zv.resize(n * K);
+  } catch (const std::exception&) {
+    fclose(f);
+    xf_set_error("checkpoint %s: not enough host memory for %llu keys", path, (unsigned long long)n);
+    return XF_ERR_IO;
+  }
   ok = fread(keys.data(), 8, n, f) == n && fread(w.data(), 4, n, f) == n;
   if (ok && has_nz) ok = fread(nw.data(), 4, n, f) == n && fread(zw.data(), 4, n, f) == n;
   if (ok && K) ok = fread(v.data(), 4, n * K, f) == n * K;

@@ -20,7 +20,7 @@
 // -------------------------------------------------------------------------------------------------
 // fill
 // -------------------------------------------------------------------------------------------------
-__global__ void xf_k_fill(uint8_t* base, uint64_t cap, uint32_t stride) {
+__global__ void xf_k_fill(uint8_t* base, uint64_t cap, uint32_t stride, int lazy) {
   // one thread per 16-byte chunk of the table
   const uint64_t chunks_per_row = stride / 16;
   const uint64_t total = cap * chunks_per_row;
@@ -29,8 +29,10 @@ __global__ void xf_k_fill(uint8_t* base, uint64_t cap, uint32_t stride) {
     uint64_t r = c / chunks_per_row;
     uint32_t q = (uint32_t)(c % chunks_per_row);
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (q == 0) { v.x = 0xFFFFFFFFu; v.y = 0xFFFFFFFFu; }
-    if (q == 1) { v.w = XF_NEG_ZERO_BITS; }  // high word of the f64 accumulator g = -0.0
+    if (q == 0) {
+      v.x = 0xFFFFFFFFu; v.y = 0xFFFFFFFFu;    // EMPTY key
+      if (!lazy) v.w = XF_NEG_ZERO_BITS;       // high word of the f64 accumulator g = -0.0 ("untouched"); lazy: integer 0
+    }
     *reinterpret_cast<uint4*>(base + r * stride + (uint64_t)q * 16) = v;
   }
 }
@@ -282,9 +284,9 @@ __global__ void xf_k_import(XfTableView t, const uint32_t* __restrict__ slots, u
     uint8_t* rowp = xf_row(t, s);
     if (c == 0) {
       if (w) {
-        *reinterpret_cast<float2*>(rowp + 8) = make_float2(w[i], nw ? nw[i] : 0.f);
-        *reinterpret_cast<float*>(rowp + 16) = zw ? zw[i] : 0.f;
-        *reinterpret_cast<unsigned long long*>(rowp + 24) = XF_NEG_ZERO_BITS64;
+        *reinterpret_cast<float2*>(rowp + XF_OFF_STATE) = make_float2(w[i], nw ? nw[i] : 0.f);
+        *reinterpret_cast<float*>(rowp + XF_OFF_STATE + 8) = zw ? zw[i] : 0.f;
+        *reinterpret_cast<unsigned long long*>(rowp + 8) = t.lazy ? 0ull : XF_NEG_ZERO_BITS64;
         if (t.lazy) *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = 0u;  // no pending step
       }
       if (v && K > 0) *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = XF_FLAG_V_READY;
@@ -412,7 +414,7 @@ int xf_tps_for(int K) {
 void xf_launch_fill(const XfTableView& t, cudaStream_t st) {
   uint64_t cap = t.mask + 1;
   uint64_t total = cap * (t.stride / 16);
-  xf_k_fill<<<xf_grid_for(total, 256, 16), 256, 0, st>>>(t.base, cap, t.stride);
+  xf_k_fill<<<xf_grid_for(total, 256, 16), 256, 0, st>>>(t.base, cap, t.stride, t.lazy);
 }
 
 template <bool SLOTG>

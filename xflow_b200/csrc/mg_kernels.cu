@@ -184,7 +184,7 @@ xf_k_pull_tokens(XfTableView t, const uint64_t* __restrict__ in_keys, const uint
     while (x >= s_pre[s + 1]) ++s;
     const uint32_t i = x - s_pre[s];
     const uint64_t key = __ldcs(in_keys + (uint64_t)s * cap + i);
-    const uint64_t home = xf_slot_hash(key, t.log2cap);
+    const uint64_t home = xf_home_slot(t, key);
     // FM rows do not change while this kernel runs (only inserts): hot rows may be served by L1
     XfHead h = FM ? xf_load_head_l1(xf_row(t, home)) : xf_load_head(xf_row(t, home));
     const int64_t r = xf_probe_from<true>(t, key, home, h);
@@ -293,19 +293,13 @@ __global__ void xf_k_bcast_rowv(const uint32_t* __restrict__ src, uint32_t n_wor
 // ---------------------------------------------------------------------------------------------------
 // owner: Push handler of ONE source rank, LR on a lazy table ("update on next touch", step_lazy.cu)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t xf_ld_tag_v(const uint8_t* rowp) {
-  uint32_t v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(rowp + XF_OFF_FLAGS));
-  return v;
-}
-
 // Every token adds its row's residual to its key's sum g; the first token of this (step, source) that
 // touches a row "opens" it: folds the pending optimizer step of the row's previous (step, source) in and
-// stamps it with `seq`.  The optimizer step of THIS push is applied by the next touch (next opener, or
-// on the fly by any reader) with divisor rows_by_seq[seq] = the source's batch size: exactly one
-// FTRL/SGD step per (source, key), sources in rank order because the S launches are stream-ordered.
-// One token per lane; lanes of a warp that hit the same row elect one opener, a winner never waits while
-// holding a claim (same deadlock-freedom argument as xf_k_step_lr_lazy).
+// stamps it with `seq` — one 128-bit CAS, xf_lazy_open in table.cuh.  The optimizer step of THIS push is
+// applied by the next touch (next opener, or on the fly by any reader) with divisor rows_by_seq[seq] = the
+// source's batch size: exactly one FTRL/SGD step per (source, key), sources in rank order because the S
+// launches are stream-ordered.  One token per lane, three row-touching instructions per token (load, CAS.128,
+// integer RED); lanes of a warp that hit the same row elect one of them.
 __global__ void __launch_bounds__(256)
 xf_k_push_tokens_lr(XfTableView t, const uint32_t* __restrict__ slots, const uint32_t* __restrict__ in_rows,
                     const float* __restrict__ rowv, const uint32_t* __restrict__ meta_s, uint32_t cap, uint32_t seq,
@@ -333,30 +327,25 @@ xf_k_push_tokens_lr(XfTableView t, const uint32_t* __restrict__ slots, const uin
     XfHead h;
     h.flags = seq;
     if (valid) h = xf_load_head(rowp);
+    // tokens of this warp that hit the same row: the lowest lane opens it and adds the group's residuals
     const unsigned grp = __match_any_sync(0xffffffffu, valid ? s : (0xFFFFFF00u | (uint32_t)lane));
     const bool lead = valid && lane == __ffs(grp) - 1;
-    const bool attempt = lead && h.flags != seq && h.flags != XF_TAG_LOCKED;
-    uint32_t prow = 1, old = 0;
-    if (attempt && h.flags) prow = __ldcg(rows_by_seq + h.flags);
-    if (attempt) old = atomicCAS(reinterpret_cast<unsigned int*>(rowp + XF_OFF_FLAGS), h.flags, XF_TAG_LOCKED);
-    const bool won = attempt && old == h.flags;
-    if (won) {
-      if (h.flags != 0u) {
-        const float g = xf_div_rows_plain((float)h.g, (double)prow);  // lr_worker.cc:116-118
-        xf_opt_coord(t, g, h.w, h.n, h.z);                             // ftrl.h:59-74 / sgd.h:52
+    unsigned long long fix = valid ? (unsigned long long)xf_fix_of(l) : 0ull;
+    if (__any_sync(0xffffffffu, valid && __popc(grp) > 1)) {
+      unsigned long long sum = 0ull;
+      for (int b = 0; b < 32; ++b) {
+        const unsigned long long o = __shfl_sync(0xffffffffu, fix, b);
+        if ((grp >> b) & 1u) sum += o;
       }
-      h.flags = seq;
-      h.g = 0.0;
-      xf_store_head(rowp, h);
-      ++open_acc;
+      fix = sum;
     }
-    __syncwarp();
-    if (lead && !won && h.flags != seq) {
-      for (int spin = 0; xf_ld_tag_v(rowp) != seq; ++spin)
-        if (spin > (1 << 22)) { *t.error = 2; break; }
+    if (lead) {
+      bool won = false;
+      unsigned long long pend = 0ull;
+      xf_lazy_open(t, rowp, h, seq, won, pend);
+      if (won) ++open_acc;
+      xf_lazy_add(rowp, fix - pend);
     }
-    __syncwarp();
-    if (valid) atomicAdd(xf_row_g(rowp), (double)l);
   }
   if (open_acc) atomicAdd(&s_open, open_acc);
   __syncthreads();

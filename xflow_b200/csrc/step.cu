@@ -109,7 +109,7 @@ xf_k_step(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* _
       const bool v0 = j0 < end, v1 = j1 < end;
       const uint64_t k0 = v0 ? __ldcs(keys + j0) : 0ull;  // streaming: do not displace table sectors in L2
       const uint64_t k1 = v1 ? __ldcs(keys + j1) : 0ull;
-      const uint64_t p0 = xf_slot_hash(k0, t.log2cap), p1 = xf_slot_hash(k1, t.log2cap);
+      const uint64_t p0 = xf_home_slot(t, k0), p1 = xf_home_slot(t, k1);
       XfHead h0, h1;
       h0.key = h1.key = XF_EMPTY_KEY;
       if (v0) h0 = FM ? xf_load_head_l1(xf_row(t, p0)) : xf_load_head(xf_row(t, p0));

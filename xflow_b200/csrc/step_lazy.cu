@@ -3,64 +3,40 @@
 // The optimizer step of batch p for a key is not applied when batch p ends; the residual sum stays in
 // the row (g, tagged p) and is folded in by the first token of a later batch b that touches the row
 // ("opening" the row for b).  Every other reader applies it on the fly (xf_apply_pending, table.cuh), so
-// the observable table is the reference's at every batch boundary.  Why: both kernels of the eager path
-// run at the DRAM random-request ceiling (43 G sectors/s, profiles/r01_randsector.md); the only lever
-// left is the number of requests, and this removes the update kernel's read + write and the step's
-// dirty write-back (17.1 M -> 9.5 M DRAM sector requests per cfg2 batch, measured with ncu).  The
-// gradient accumulation must stay in the same kernel as the open: run as a second kernel it finds the
-// rows evicted again (measured: +180 us).
+// the observable table is the reference's at every batch boundary.
 //
-// Protocol per row, batch b (tag = the row's flags word):
+// Why: on a multi-GB table every row-touching instruction costs about the same (~28 ps of chip time: load,
+// store or atomic, hit or miss — tools/membench.cu, profiles/r02_membench.md), so the kernel's time is
+// (row-touching instructions per token) x 28 ps x tokens.  The eager pair (step + update) needs 4.3 per token,
+// round 1's lazy protocol (load, CAS on the tag, 256-bit store, RED) also 4.3 but in one launch; this one needs
+// 3.3: load (1.3 with the collision probes), ONE 128-bit CAS that claims and publishes, one integer RED.
+//
+// Protocol per row, batch b (tag = the row's flags word; xf_lazy_open in table.cuh):
 //   tag == b              open for b: w is current, g accumulates batch b.
-//   tag == p (0 < p < b)  pending: exactly one token wins atomicCAS(tag, p, LOCKED), applies
-//   tag == 0              FTRL/SGD(g / rows[p]) (nothing for 0), and publishes {w,n,z, tag = b, g = 0}
-//                         with one 256-bit store.  Nobody else writes the row while it is LOCKED.
-//   tag == LOCKED         another token is opening: poll until tag == b, then read w.
-// Rules that keep it deadlock-free: a winner publishes immediately (it never waits while holding a
-// claim, for either of its two tokens); inside a warp, tokens with the same slot elect one lane
-// (__match_any_sync) so a warp never waits on itself.  The same groups let one lane add
-// count x residual in phase B.  Waits are bounded (error code 2 instead of a hung GPU).
+//   tag == p (p < b)      pending (p == 0: nothing pending): the token computes the row's new state from its
+//                         snapshot (FTRL/SGD step with g / rows[p]) and tries
+//                         CAS.128({w,n,z,tag}: snapshot -> {w',n',z', b}).  Exactly one token of the batch
+//                         succeeds; the others are handed the published state back by their failed CAS.
+//                         Nobody ever waits: there is no locked state.
+//   g                     64-bit fixed-point residual sum (scale 2^40).  The opener owes the row "- g_pending";
+//                         it pays in the same RED that adds its own residual after the row reduction
+//                         (integer adds commute exactly, so the order in which REDs land is irrelevant and the
+//                         result is bit-reproducible).
+// Inside a warp, tokens with the same slot elect one lane (__match_any_sync): one open and one RED of
+// count x residual per distinct key of a 32-token group.
 //
-// The kernel is dependency-chain bound, not bandwidth bound (ncu: DRAM 10 %, L2 24 %, issue 15 % busy;
-// ablation: read-only pass 190 us, + claim/publish 130 us, + accumulate 75 us): see DESIGN.md section 6.
+// Tried and measured on the 1e8-id table (profiles/r02_lazy_experiments.md): bucketised probing (collision
+// probes inside one 128-byte line: -3 %, kept), L2 prefetch by dedicated warps running ahead (+23 % time: the
+// prefetches are requests too, removed).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "table.cuh"
 
 #define XF_NO_SLOT 0xFFFFFFFFu
-
-__device__ __forceinline__ uint32_t xf_ld_tag(const uint8_t* rowp) {
-  uint32_t v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(rowp + XF_OFF_FLAGS));
-  return v;
-}
-
-// volatile 256-bit re-read of a row whose tag this thread has just observed to be `seq`
-__device__ __forceinline__ float xf_reload_w(const uint8_t* rowp) {
-  uint64_t q0, q1, q2, q3;
-  asm volatile("ld.volatile.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(rowp));
-  (void)q0; (void)q2; (void)q3;
-  return __uint_as_float((uint32_t)q1);
-}
-
-// poll until the row is open for `seq` (its opener never waits, so this ends within a store latency)
-__device__ __forceinline__ void xf_wait_open(const XfTableView& t, const uint8_t* rowp, uint32_t seq) {
-  for (int spin = 0; xf_ld_tag(rowp) != seq; ++spin) {
-    if (spin > (1 << 22)) { *t.error = 2; break; }
-  }
-}
-
-// fold the pending step (batch h.flags, `rows` rows) into the snapshot and stamp it open for `seq`
-__device__ __forceinline__ void xf_open_snapshot(const XfTableView& t, XfHead& h, uint32_t rows, uint32_t seq) {
-  if (h.flags != 0u) {
-    const float g = xf_div_rows_plain((float)h.g, (double)rows);  // lr_worker.cc:116-118 (the fast path spills here)
-    xf_opt_coord(t, g, h.w, h.n, h.z);                       // ftrl.h:59-74 / sgd.h:52
-  }
-  h.flags = seq;
-  h.g = 0.0;
-}
+#define XF_LAZY_CACHED 2  // 64-token chunks whose leader slots stay in registers between the two phases
 
 __global__ void __launch_bounds__(256)
 xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* __restrict__ keys,
@@ -84,8 +60,17 @@ xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uin
     const uint32_t end = __ldg(row_ptr + row + 1);
     const int chunks = (int)((end - beg + 63u) >> 6);
     float wsum = 0.f;
-    uint32_t lead_s0 = XF_NO_SLOT, lead_s1 = XF_NO_SLOT;  // first chunk: slot if this lane leads its group
-    uint32_t cnt_c = 0;                                    //              and the group sizes (8 bits each)
+    // first XF_LAZY_CACHED chunks (rows <= 128 tokens), per half: the slot if this lane leads its group, the group
+    // size, and what the lane owes the row if it opened it
+    uint32_t lead_s[2 * XF_LAZY_CACHED];
+    uint32_t cnt_c[XF_LAZY_CACHED];  // 8 bits per half
+    unsigned long long pend_c[2 * XF_LAZY_CACHED];
+#pragma unroll
+    for (int c = 0; c < XF_LAZY_CACHED; ++c) {
+      lead_s[2 * c] = lead_s[2 * c + 1] = XF_NO_SLOT;
+      pend_c[2 * c] = pend_c[2 * c + 1] = 0ull;
+      cnt_c[c] = 0;
+    }
 
     // ---------------- phase A: pull (and, in training, open) every token's row
     for (int ch = 0; ch < chunks; ++ch) {
@@ -94,7 +79,7 @@ xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uin
       const bool v0 = j0 < end, v1 = j1 < end;
       const uint64_t k0 = v0 ? __ldcs(keys + j0) : 0ull;
       const uint64_t k1 = v1 ? __ldcs(keys + j1) : 0ull;
-      const uint64_t p0 = xf_slot_hash(k0, t.log2cap), p1 = xf_slot_hash(k1, t.log2cap);
+      const uint64_t p0 = xf_home_slot(t, k0), p1 = xf_home_slot(t, k1);
       XfHead h0, h1;
       h0.key = h1.key = XF_EMPTY_KEY;
       h0.flags = h1.flags = 0u;
@@ -105,6 +90,7 @@ xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uin
       if (v1) { const int64_t r = xf_probe_from<true>(t, k1, p1, h1); if (r >= 0) s1 = (uint32_t)r; }
       float w0 = 0.f, w1 = 0.f;
       uint32_t cnt0 = 0, cnt1 = 0;
+      unsigned long long pend0 = 0ull, pend1 = 0ull;
       if (mode == 1) {
         // forward only: apply a pending step on the fly, write nothing
         if (s0 != XF_NO_SLOT) { xf_apply_pending(t, h0); w0 = h0.w; }
@@ -115,45 +101,31 @@ xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uin
         const unsigned grp1 = __match_any_sync(0xffffffffu, (s1 != XF_NO_SLOT) ? s1 : (0xFFFFFF00u | (uint32_t)lane));
         const int lead0 = __ffs(grp0) - 1, lead1 = __ffs(grp1) - 1;
         const bool L0 = s0 != XF_NO_SLOT && lane == lead0, L1 = s1 != XF_NO_SLOT && lane == lead1;
-        uint8_t* r0 = xf_row(t, s0);
-        uint8_t* r1 = xf_row(t, s1);
-        const bool try0 = L0 && h0.flags != seq && h0.flags != XF_TAG_LOCKED;
-        const bool try1 = L1 && h1.flags != seq && h1.flags != XF_TAG_LOCKED;
-        // divisors of the pending steps and both claims are issued before any result is consumed
-        uint32_t prow0 = 1, prow1 = 1, old0 = 0, old1 = 0;
-        if (try0 && h0.flags) prow0 = __ldg(t.rows_by_seq + h0.flags);
-        if (try1 && h1.flags) prow1 = __ldg(t.rows_by_seq + h1.flags);
-        if (try0) old0 = atomicCAS(reinterpret_cast<unsigned int*>(r0 + XF_OFF_FLAGS), h0.flags, XF_TAG_LOCKED);
-        if (try1) old1 = atomicCAS(reinterpret_cast<unsigned int*>(r1 + XF_OFF_FLAGS), h1.flags, XF_TAG_LOCKED);
-        // Winners publish at once, for both halves, BEFORE anybody waits: a claim is never held across a
-        // wait (holding the half-1 claim while spinning on a half-0 row deadlocked two warps).
-        const bool won0 = try0 && old0 == h0.flags;
-        const bool won1 = try1 && old1 == h1.flags;
-        if (won0) { xf_open_snapshot(t, h0, prow0, seq); xf_store_head(r0, h0); ++open_acc; }
-        if (won1) { xf_open_snapshot(t, h1, prow1, seq); xf_store_head(r1, h1); ++open_acc; }
-        __syncwarp();
-        if (L0) {
-          w0 = h0.w;
-          if (!won0 && h0.flags != seq) { xf_wait_open(t, r0, seq); w0 = xf_reload_w(r0); }
-          cnt0 = (uint32_t)__popc(grp0);
-        }
-        if (L1) {
-          w1 = h1.w;
-          if (!won1 && h1.flags != seq) { xf_wait_open(t, r1, seq); w1 = xf_reload_w(r1); }
-          cnt1 = (uint32_t)__popc(grp1);
-        }
+        bool won0 = false, won1 = false;
+        if (L0) { w0 = xf_lazy_open(t, xf_row(t, s0), h0, seq, won0, pend0); cnt0 = (uint32_t)__popc(grp0); }
+        if (L1) { w1 = xf_lazy_open(t, xf_row(t, s1), h1, seq, won1, pend1); cnt1 = (uint32_t)__popc(grp1); }
+        open_acc += (won0 ? 1u : 0u) + (won1 ? 1u : 0u);
         w0 = __shfl_sync(0xffffffffu, w0, lead0);
         w1 = __shfl_sync(0xffffffffu, w1, lead1);
         if (s0 == XF_NO_SLOT) w0 = 0.f;
         if (s1 == XF_NO_SLOT) w1 = 0.f;
+        if (ch >= XF_LAZY_CACHED) {
+          // long rows (> 128 tokens): nothing is remembered for phase B, the opener pays its debt at once
+          if (won0) xf_lazy_add(xf_row(t, s0), 0ull - pend0);
+          if (won1) xf_lazy_add(xf_row(t, s1), 0ull - pend1);
+        }
       }
       wsum += w0;
       wsum += w1;
-      if (ch == 0) {
-        lead_s0 = cnt0 ? s0 : XF_NO_SLOT;
-        lead_s1 = cnt1 ? s1 : XF_NO_SLOT;
-        cnt_c = cnt0 | (cnt1 << 8);
-      }
+#pragma unroll
+      for (int c = 0; c < XF_LAZY_CACHED; ++c)
+        if (ch == c) {
+          lead_s[2 * c] = cnt0 ? s0 : XF_NO_SLOT;
+          lead_s[2 * c + 1] = cnt1 ? s1 : XF_NO_SLOT;
+          pend_c[2 * c] = pend0;
+          pend_c[2 * c + 1] = pend1;
+          cnt_c[c] = cnt0 | (cnt1 << 8);
+        }
     }
 
     const float wx = xf_warp_sum(wsum);
@@ -166,18 +138,23 @@ xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uin
     if (lane == 0 && loss_out) loss_out[row] = loss;
     abs_acc += fabsf(loss);
     // ---------------- phase B: residual into the per-key sums (every row is open for `seq`); the rows
-    // are L2-resident right now, which is why this is not a separate kernel
-    const double gd = (double)loss;
-    // one lane per distinct slot of the round adds count x residual (exact in double)
-    if (lead_s0 != XF_NO_SLOT) atomicAdd(xf_row_g(xf_row(t, lead_s0)), gd * (double)(cnt_c & 0xFFu));
-    if (lead_s1 != XF_NO_SLOT) atomicAdd(xf_row_g(xf_row(t, lead_s1)), gd * (double)(cnt_c >> 8));
-    for (int ch = 1; ch < chunks; ++ch) {
-      // long rows (> 64 tokens): slots are not cached; the rows were opened in phase A
+    // are L2-resident right now, which is why this is not a separate kernel.  One lane per distinct slot of a
+    // group adds count x residual (minus what it owes as the row's opener): integer, exact.
+    const unsigned long long lf = (unsigned long long)xf_fix_of(loss);
+#pragma unroll
+    for (int c = 0; c < XF_LAZY_CACHED; ++c) {
+      if (lead_s[2 * c] != XF_NO_SLOT)
+        xf_lazy_add(xf_row(t, lead_s[2 * c]), lf * (unsigned long long)(cnt_c[c] & 0xFFu) - pend_c[2 * c]);
+      if (lead_s[2 * c + 1] != XF_NO_SLOT)
+        xf_lazy_add(xf_row(t, lead_s[2 * c + 1]), lf * (unsigned long long)(cnt_c[c] >> 8) - pend_c[2 * c + 1]);
+    }
+    for (int ch = XF_LAZY_CACHED; ch < chunks; ++ch) {
+      // long rows (> 128 tokens): slots are not cached; the rows were opened in phase A
       const uint32_t j0 = beg + (uint32_t)ch * 64u + (uint32_t)lane;
       const uint32_t j1 = j0 + 32u;
       XfHead h;
-      if (j0 < end) { const int64_t r = xf_probe<false>(t, __ldg(keys + j0), &h); if (r >= 0) atomicAdd(xf_row_g(xf_row(t, (uint64_t)r)), gd); }
-      if (j1 < end) { const int64_t r = xf_probe<false>(t, __ldg(keys + j1), &h); if (r >= 0) atomicAdd(xf_row_g(xf_row(t, (uint64_t)r)), gd); }
+      if (j0 < end) { const int64_t r = xf_probe<false>(t, __ldg(keys + j0), &h); if (r >= 0) xf_lazy_add(xf_row(t, (uint64_t)r), lf); }
+      if (j1 < end) { const int64_t r = xf_probe<false>(t, __ldg(keys + j1), &h); if (r >= 0) xf_lazy_add(xf_row(t, (uint64_t)r), lf); }
     }
   }
   if (mode == 0) {
