@@ -104,3 +104,62 @@ def test_ps_lite_shaped_surface_on_the_device(tmp_path):
     from common import build_and_run_ps_compat
     r = build_and_run_ps_compat(tmp_path)
     assert r.returncode == 0 and "transport ok" in r.stdout and "device handles ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("model,K", [("0", 0), ("1", 10)])
+def test_cli_two_ranks_train_against_the_sharded_table(model, K, tmp_path):
+    """The reference's launch shape (local.sh: N worker processes, rank = ps::MyRank(), every rank trains
+    <train>-%05d against the SHARED servers, main.cc:15-48, lr_worker.cc:207-217) on two GPUs: two xflow_lr processes
+    with XFLOW_RANK / XFLOW_WORLD find each other through a file, each owns one key range of the table, rank 0
+    predicts through the sharded forward pass.  Compared with the oracle's lock-step schedule on one table."""
+    if api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import oracle as O
+    exe = os.path.join(ROOT, "xflow_b200", "bin", "xflow_lr")
+    # two train shards: the golden shard cut in two (rank 1 gets fewer rows AND its own block count)
+    lines = open(TRAIN + "-00000", "rb").read().splitlines(keepends=True)
+    prefix = str(tmp_path / "train")
+    open(prefix + "-00000", "wb").write(b"".join(lines[:120]))
+    open(prefix + "-00001", "wb").write(b"".join(lines[120:]))
+    epochs = 5
+    procs = []
+    for rank in range(2):
+        cwd = tmp_path / ("rank%d" % rank)
+        cwd.mkdir()
+        env = dict(os.environ, XFLOW_OPTIMIZER="ftrl", XFLOW_RANK=str(rank), XFLOW_WORLD="2", XFLOW_DEVICE=str(rank),
+                   XFLOW_COMM_FILE=str(tmp_path / "comm.id"), XFLOW_MG_TIMEOUT_S="60", XFLOW_SEED="0")
+        procs.append((cwd, subprocess.Popen([exe, prefix, TEST, model, str(epochs)], cwd=str(cwd), env=env,
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    outs = []
+    for cwd, p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, out
+        outs.append(out)
+    assert "my rank is = 0" in outs[0] and "my rank is = 1" in outs[1]
+    assert "logloss" in outs[0] and "logloss" not in outs[1]          # only rank 0 predicts and prints
+    assert not os.path.exists(str(tmp_path / "rank1" / "pred_1_0.txt")) or os.path.getsize(str(tmp_path / "rank1" / "pred_1_0.txt")) == 0
+    ll, auc, tp, fp = _parse(outs[0])
+    # the oracle: one table, every worker computes from the same state, pushes land in rank order
+    t = O.Table(K=K, opt=O.OPT_FTRL, init_mode=O.INIT_COUNTER, seed=0)
+    for _ in range(2):
+        t.init_push()
+    shards = [next(iter(O.load_blocks(prefix + "-%05d" % r, 2 << 20))) for r in range(2)]
+    for _ in range(epochs):
+        pend = [t.worker_compute(rp, keys, lab) for rp, keys, lab in shards]
+        for uk, gw, gv, _ in pend:
+            t.push(uk, gw, gv if K else None)
+    lab, p = O.predict_file(t, TEST + "-00000", (4 << 20) if K == 0 else (2 << 20))
+    m = O.auc_logloss(lab, p)
+    assert tp + fp == lab.size
+    assert abs(ll - m["logloss"]) <= 2e-5 * abs(m["logloss"]) + 1e-6
+    assert abs(auc - m["auc"]) <= 2e-5
+    pred = np.loadtxt(str(tmp_path / "rank0" / "pred_0_0.txt"), ndmin=2)
+    assert np.all(np.abs(pred[:, 0] - p) <= 2e-5 * np.abs(p) + 1.1e-6)
+
+
+def test_rank_without_world_is_refused(tmp_path):
+    exe = os.path.join(ROOT, "xflow_b200", "bin", "xflow_lr")
+    env = dict(os.environ, XFLOW_RANK="1")
+    env.pop("XFLOW_WORLD", None); env.pop("WORLD_SIZE", None)
+    r = subprocess.run([exe, TRAIN, TEST, "0", "1"], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "XFLOW_WORLD" in (r.stdout + r.stderr)

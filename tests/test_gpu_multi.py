@@ -147,7 +147,9 @@ def test_sharded_step_matches_lockstep_oracle(world, name, tmp_path):
         assert got["uniq"] == uniq[r], "rank %d: unique keys counted by the owners" % r   # dedup is exact
         for a, b, c in zip(got["losses"], ref_losses[r], ex_losses[r]):
             if skew:
-                assert_close_noise_aware(a, b, c, "loss rank %d" % r, abs_floor=1e-6, max_noisy_frac=0.05)
+                # a hot key's reference noise shows in every row that holds the key (17 % of the rows at 8 ranks, also
+                # for a float64 numpy model of the protocol): each row must be inside 8x that noise, their share is free
+                assert_close_noise_aware(a, b, c, "loss rank %d" % r, abs_floor=1e-6, max_noisy_frac=1.0)
             else:
                 assert_close(a, b, "loss rank %d" % r, abs_floor=1e-6)
         ref, refx = t.export(got["keys"]), tx.export(got["keys"])
@@ -173,6 +175,6 @@ def test_sharded_step_matches_lockstep_oracle(world, name, tmp_path):
         _, _, _, lossx = tx.worker_compute(rp.astype(np.int64), keys, lab.astype(np.int32))
         if skew:
             assert_close_noise_aware(ret[r]["pctr"], loss.astype(np.float64) + lab, lossx.astype(np.float64) + lab,
-                                     "pctr rank %d" % r, abs_floor=1e-6, max_noisy_frac=0.05)
+                                     "pctr rank %d" % r, abs_floor=1e-6, max_noisy_frac=1.0)
         else:
             assert_close(ret[r]["pctr"], loss.astype(np.float64) + lab, "pctr rank %d" % r, abs_floor=1e-6)

@@ -213,6 +213,7 @@ struct XfMg {
   XfPeers peers;            // every rank's slab as mapped here (peers.slab[rank] == slab)
   XfDevBuf slots, tok_pos[2], bucket_cnt[2], rowv_local, touched;
   XfDevBuf side_v;  // FM, S > 1: latent rows as pulled by the tokens of sources >= 1 (see xf_k_pull_tokens)
+  XfDevBuf stash;   // LR, lazy table: the 32-byte row of every routed token as the Pull found it, for the Push
   uint32_t touched_extra = 0;
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_rows_done[2] = {nullptr, nullptr};  // tok_pos[p] no longer read by the table stream
@@ -323,6 +324,10 @@ int xf_mg_create(xf_trainer* tr) {
     if ((rc = mg->slots.ensure((size_t)S * mg->cap * 4)) != XF_OK) break;
     if ((rc = mg->rowv_local.ensure((size_t)mg->max_rows * 8 + 16)) != XF_OK) break;
     const bool lazy = tr->table->view.lazy != 0;
+    {
+      const char* se = getenv("XFLOW_MG_STASH");  // A/B: 0 = the Push handler loads the rows itself
+      if (lazy && !(se && *se == '0') && (rc = mg->stash.ensure((size_t)S * mg->cap * 32)) != XF_OK) break;
+    }
     if (!lazy) {
       mg->touched_extra = xf_acc_touched_extra(mg->K, (uint64_t)mg->cap);
       if ((rc = mg->touched.ensure(((size_t)mg->cap + 2 * (size_t)mg->touched_extra) * 4)) != XF_OK) break;
@@ -393,7 +398,7 @@ void xf_mg_destroy(xf_trainer* tr) {
     }
   }
   if (mg->slab) cudaFree(mg->slab);
-  mg->slots.release(); mg->rowv_local.release(); mg->touched.release(); mg->side_v.release();
+  mg->slots.release(); mg->rowv_local.release(); mg->touched.release(); mg->side_v.release(); mg->stash.release();
   for (int b = 0; b < 2; ++b) {
     mg->tok_pos[b].release(); mg->bucket_cnt[b].release();
     if (mg->ev_rows_done[b]) cudaEventDestroy(mg->ev_rows_done[b]);
@@ -469,7 +474,8 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
   if (pm) XF_CUDA_TRY(cudaEventRecord(pm[0], st));
   xf_launch_pull_tokens(t->view, reinterpret_cast<const uint64_t*>(mg->slab + off_keys_p), meta_p, S, me, cap,
                         (uint64_t)nnz + 1, mg->peers, L.off_vals, mg->slots.as<uint32_t>(),
-                        (mode == 0 && mg->side_v.p) ? mg->side_v.as<float>() : nullptr, st);
+                        (mode == 0 && mg->side_v.p) ? mg->side_v.as<float>() : nullptr,
+                        mode == 0 ? mg->stash.p : nullptr, st);
   if (pm) XF_CUDA_TRY(cudaEventRecord(pm[1], st));
   {
     const int slot = (int)(step & 3);
@@ -525,7 +531,8 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
     if (t->view.lazy) {
       XF_TRY(t->next_seq());
       xf_launch_push_tokens_lr(t->view, slots_s, rows_s, reinterpret_cast<const float*>(rowv_s), meta_s, cap, work, t->seq,
-                               t->d_rows_by_seq, uniq_s, st);
+                               t->d_rows_by_seq, uniq_s,
+                               mg->stash.p ? (const uint8_t*)mg->stash.p + (size_t)s * cap * 32 : nullptr, st);
       ++tr->launches;
     } else {
       xf_launch_acc_tokens(t->view, slots_s, rows_s, rowv_s, meta_s, cap, work, mg->touched.as<uint32_t>(), st);

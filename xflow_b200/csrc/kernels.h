@@ -53,7 +53,7 @@ void xf_launch_route(const uint32_t* row_ptr, const uint64_t* keys, uint32_t row
                      uint32_t* bucket_cnt, uint32_t* tok_pos, cudaStream_t st);
 void xf_launch_pull_tokens(const XfTableView& t, const uint64_t* in_keys, const uint32_t* meta, int S, int me,
                            uint32_t cap, uint64_t work_bound, const XfPeers& peers, uint64_t off_vals,
-                           uint32_t* slots, float* side_v, cudaStream_t st);
+                           uint32_t* slots, float* side_v, void* stash, cudaStream_t st);
 void xf_launch_rows(bool fm, const uint32_t* row_ptr, const uint8_t* labels, int B, int mode, const uint32_t* tok_pos,
                     const void* vals, float* rowv, float* loss_out, float* pctr_out, float* abs_loss_sum,
                     cudaStream_t st);
@@ -61,7 +61,8 @@ void xf_launch_bcast_rowv(const float* src, uint32_t n_words, int S, const XfPee
                           uint64_t dst_word_off, cudaStream_t st);
 void xf_launch_push_tokens_lr(const XfTableView& t, const uint32_t* slots, const uint32_t* in_rows, const float* rowv,
                               const uint32_t* meta_s, uint32_t cap, uint64_t work_bound, uint32_t seq,
-                              uint32_t* rows_by_seq, unsigned long long* uniq_remote, cudaStream_t st);
+                              uint32_t* rows_by_seq, unsigned long long* uniq_remote, const void* stash,
+                              cudaStream_t st);
 uint32_t xf_acc_touched_extra(int K, uint64_t work_bound);
 void xf_launch_acc_tokens(const XfTableView& t, const uint32_t* slots, const uint32_t* in_rows, const void* rowv,
                           const uint32_t* meta_s, uint32_t cap, uint64_t work_bound, uint32_t* touched,

@@ -169,7 +169,7 @@ template <bool FM, int VEC>
 __global__ void __launch_bounds__(256)
 xf_k_pull_tokens(XfTableView t, const uint64_t* __restrict__ in_keys, const uint32_t* __restrict__ meta, int S, int me,
                  uint32_t cap, XfPeers peers, uint64_t off_vals, uint32_t* __restrict__ slots,
-                 float* __restrict__ side_v) {
+                 float* __restrict__ side_v, uint4* __restrict__ stash) {
   __shared__ uint32_t s_pre[XF_MG_MAX_SHARDS + 1];
   if (threadIdx.x == 0) {
     uint32_t o = 0;
@@ -189,12 +189,34 @@ xf_k_pull_tokens(XfTableView t, const uint64_t* __restrict__ in_keys, const uint
     XfHead h = FM ? xf_load_head_l1(xf_row(t, home)) : xf_load_head(xf_row(t, home));
     const int64_t r = xf_probe_from<true>(t, key, home, h);
     float w = 0.f, st = 0.f, qt = 0.f;
+    if (!FM && stash != nullptr) {
+      // LR, lazy table: the row exactly as found goes to the Push handler of this step (streaming, 32 B per
+      // token): its open then needs no load of the row — one row-touching instruction less per token
+      XfHead raw = h;
+      if (r < 0) raw.key = XF_EMPTY_KEY;
+      uint4* sp = stash + 2 * ((uint64_t)s * cap + i);
+      __stcs(sp, make_uint4((uint32_t)raw.key, (uint32_t)(raw.key >> 32), (uint32_t)__double_as_longlong(raw.g),
+                            (uint32_t)((unsigned long long)__double_as_longlong(raw.g) >> 32)));
+      __stcs(sp + 1, make_uint4(__float_as_uint(raw.w), __float_as_uint(raw.n), __float_as_uint(raw.z), raw.flags));
+    }
     if (r >= 0) {
       xf_apply_pending(t, h);  // lazy LR tables: the value the reference's server would hold
       w = h.w;
       if (FM) {
         float* sv = (s > 0 && side_v != nullptr) ? side_v + ((uint64_t)s * cap + i) * (uint64_t)K : nullptr;
-        if (h.flags & XF_FLAG_V_READY) {
+        if ((h.flags & XF_FLAG_V_READY) && (K & 7) == 0) {
+          const float* vp = reinterpret_cast<const float*>(xf_row(t, (uint64_t)r) + 32);
+          for (int k = 0; k < K; k += 8) {  // 256-bit loads: half as many row-touching instructions
+            float v[8];
+            xf_ld8_l1(vp + k, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { st += v[e]; qt = __fadd_rn(qt, __fmul_rn(v[e], v[e])); }
+            if (sv) {
+              __stcs(reinterpret_cast<float4*>(sv + k), make_float4(v[0], v[1], v[2], v[3]));
+              __stcs(reinterpret_cast<float4*>(sv + k + 4), make_float4(v[4], v[5], v[6], v[7]));
+            }
+          }
+        } else if (h.flags & XF_FLAG_V_READY) {
           const float* vp = reinterpret_cast<const float*>(xf_row(t, (uint64_t)r) + 32);
           for (int k = 0; k < K; k += VEC) {
             float v[VEC];
@@ -303,7 +325,7 @@ __global__ void xf_k_bcast_rowv(const uint32_t* __restrict__ src, uint32_t n_wor
 __global__ void __launch_bounds__(256)
 xf_k_push_tokens_lr(XfTableView t, const uint32_t* __restrict__ slots, const uint32_t* __restrict__ in_rows,
                     const float* __restrict__ rowv, const uint32_t* __restrict__ meta_s, uint32_t cap, uint32_t seq,
-                    uint32_t* rows_by_seq, unsigned long long* uniq_remote) {
+                    uint32_t* rows_by_seq, unsigned long long* uniq_remote, const uint4* __restrict__ stash) {
   __shared__ unsigned int s_open;
   if (threadIdx.x == 0) s_open = 0;
   const uint32_t n = min(__ldg(meta_s), cap);
@@ -326,7 +348,17 @@ xf_k_push_tokens_lr(XfTableView t, const uint32_t* __restrict__ slots, const uin
     uint8_t* rowp = xf_row(t, valid ? s : 0);
     XfHead h;
     h.flags = seq;
-    if (valid) h = xf_load_head(rowp);
+    if (valid) {
+      if (stash != nullptr) {
+        // the row as this step's Pull found it (coalesced, streaming) instead of a load of the row itself
+        const uint4 a = __ldcs(stash + 2 * (uint64_t)i), b = __ldcs(stash + 2 * (uint64_t)i + 1);
+        h.key = (uint64_t)a.x | ((uint64_t)a.y << 32);
+        h.g = __longlong_as_double((long long)((uint64_t)a.z | ((uint64_t)a.w << 32)));
+        h.w = __uint_as_float(b.x); h.n = __uint_as_float(b.y); h.z = __uint_as_float(b.z); h.flags = b.w;
+      } else {
+        h = xf_load_head(rowp);
+      }
+    }
     // tokens of this warp that hit the same row: the lowest lane opens it and adds the group's residuals
     const unsigned grp = __match_any_sync(0xffffffffu, valid ? s : (0xFFFFFF00u | (uint32_t)lane));
     const bool lead = valid && lane == __ffs(grp) - 1;
@@ -340,9 +372,14 @@ xf_k_push_tokens_lr(XfTableView t, const uint32_t* __restrict__ slots, const uin
       fix = sum;
     }
     if (lead) {
-      bool won = false;
+      bool won = false, stale = false;
       unsigned long long pend = 0ull;
-      xf_lazy_open(t, rowp, h, seq, won, pend);
+      xf_lazy_open(t, rowp, h, seq, won, pend, stash != nullptr ? &stale : nullptr);
+      if (stale) {
+        // an earlier source of this round (or an earlier launch) changed the row since the Pull: take a fresh look
+        h = xf_load_head(rowp);
+        xf_lazy_open(t, rowp, h, seq, won, pend);
+      }
       if (won) ++open_acc;
       xf_lazy_add(rowp, fix - pend);
     }
@@ -475,9 +512,9 @@ void xf_launch_route(const uint32_t* row_ptr, const uint64_t* keys, uint32_t row
 }
 void xf_launch_pull_tokens(const XfTableView& t, const uint64_t* in_keys, const uint32_t* meta, int S, int me,
                            uint32_t cap, uint64_t work_bound, const XfPeers& peers, uint64_t off_vals,
-                           uint32_t* slots, float* side_v, cudaStream_t st) {
+                           uint32_t* slots, float* side_v, void* stash, cudaStream_t st) {
   const int grid = xf_grid_for(work_bound ? work_bound : 1, 256, 8);
-#define XF_PT_ARGS t, in_keys, meta, S, me, cap, peers, off_vals, slots, side_v
+#define XF_PT_ARGS t, in_keys, meta, S, me, cap, peers, off_vals, slots, side_v, reinterpret_cast<uint4*>(stash)
   if (t.K == 0) {
     xf_k_pull_tokens<false, 1><<<grid, 256, 0, st>>>(XF_PT_ARGS);
   } else {
@@ -506,9 +543,11 @@ void xf_launch_bcast_rowv(const float* src, uint32_t n_words, int S, const XfPee
 }
 void xf_launch_push_tokens_lr(const XfTableView& t, const uint32_t* slots, const uint32_t* in_rows, const float* rowv,
                               const uint32_t* meta_s, uint32_t cap, uint64_t work_bound, uint32_t seq,
-                              uint32_t* rows_by_seq, unsigned long long* uniq_remote, cudaStream_t st) {
+                              uint32_t* rows_by_seq, unsigned long long* uniq_remote, const void* stash,
+                              cudaStream_t st) {
   const int grid = xf_grid_for(work_bound ? work_bound : 1, 256, 8);
-  xf_k_push_tokens_lr<<<grid, 256, 0, st>>>(t, slots, in_rows, rowv, meta_s, cap, seq, rows_by_seq, uniq_remote);
+  xf_k_push_tokens_lr<<<grid, 256, 0, st>>>(t, slots, in_rows, rowv, meta_s, cap, seq, rows_by_seq, uniq_remote,
+                                             reinterpret_cast<const uint4*>(stash));
 }
 // extra touched[] ENTRIES the accumulation kernel appends beyond cap (grid x NC); it needs twice that many
 // positions (the entries' representative tokens follow them)

@@ -184,6 +184,17 @@ __device__ __forceinline__ XfHead xf_load_head_l1(const uint8_t* row) {
   return h;
 }
 
+// eight consecutive floats of a latent row with ONE 256-bit load through L1 (read-only-for-the-kernel data,
+// see xf_load_head_l1): a row access costs per instruction, not per byte (tools/membench.cu)
+__device__ __forceinline__ void xf_ld8_l1(const float* p, float (&o)[8]) {
+  uint64_t q0, q1, q2, q3;
+  asm volatile("ld.global.ca.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(p));
+  o[0] = __uint_as_float((uint32_t)q0); o[1] = __uint_as_float((uint32_t)(q0 >> 32));
+  o[2] = __uint_as_float((uint32_t)q1); o[3] = __uint_as_float((uint32_t)(q1 >> 32));
+  o[4] = __uint_as_float((uint32_t)q2); o[5] = __uint_as_float((uint32_t)(q2 >> 32));
+  o[6] = __uint_as_float((uint32_t)q3); o[7] = __uint_as_float((uint32_t)(q3 >> 32));
+}
+
 // full-sector store of the head (one 256-bit STG: no partial-sector write, no read-for-fill)
 __device__ __forceinline__ void xf_store_head(uint8_t* row, const XfHead& h) {
   const uint64_t q1 = (uint64_t)__double_as_longlong(h.g);
@@ -348,10 +359,14 @@ __device__ __forceinline__ bool xf_cas_state(uint8_t* rowp, const XfState& expec
 // sum: `pend` = the raw 64 bits of g in its snapshot, to be subtracted in the same RED that adds the token's own
 // residual (integer arithmetic mod 2^64: exact, whatever lands in between).  g of the snapshot is final when the
 // CAS succeeds: residuals of batch `seq` are only added to rows that were seen open, i.e. after this CAS.
+// `stale` (optional): the caller's snapshot may be OLDER than this batch (the sharded owner keeps the snapshot its
+// Pull took, mg_kernels.cu); a CAS that fails against a row which is not open for `seq` then reports *stale = true
+// instead of an error, and the caller reloads the row and tries again.
 __device__ __forceinline__ float xf_lazy_open(const XfTableView& t, uint8_t* rowp, const XfHead& h, uint32_t seq,
-                                              bool& won, unsigned long long& pend) {
+                                              bool& won, unsigned long long& pend, bool* stale = nullptr) {
   won = false;
   pend = 0ull;
+  if (stale) *stale = false;
   if (h.flags == seq) return h.w;
   XfState e{h.w, h.n, h.z, h.flags}, d = e, f;
   if (h.flags != 0u) xf_fold_pending(t, xf_head_gfix(h), __ldg(t.rows_by_seq + h.flags), d.w, d.n, d.z);
@@ -361,7 +376,10 @@ __device__ __forceinline__ float xf_lazy_open(const XfTableView& t, uint8_t* row
     pend = (unsigned long long)__double_as_longlong(h.g);
     return d.w;
   }
-  if (f.flags != seq) *t.error = 2;  // inside a batch a row only ever goes from "pending" to "open for seq"
+  if (f.flags != seq) {
+    if (stale) *stale = true;
+    else *t.error = 2;  // inside a batch a row only ever goes from "pending" to "open for seq"
+  }
   return f.w;
 }
 __device__ __forceinline__ void xf_lazy_add(uint8_t* rowp, unsigned long long fix) {
