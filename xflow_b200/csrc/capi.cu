@@ -150,7 +150,7 @@ int xf_table::grow(uint64_t new_capacity) {
 // Lazy tables number their batches (sharded: every (step, source) pair) with `seq`; rows_by_seq[seq] is the
 // divisor of that batch's pending optimizer steps.  The array is a fixed ring: when the numbers run out,
 // one sweep folds every pending step into its row (xf_k_flush_pending, stream-ordered, no host sync) and
-// the numbering restarts at 1 — no reallocation, no 32-bit wrap into XF_TAG_LOCKED.
+// the numbering restarts at 1 — no reallocation, and the batch tag fits the 16 bits a lazy row has for it.
 int xf_table::next_seq() {
   if ((size_t)seq + 1 >= rows_cap) {
     xf_launch_flush_pending(view, stream);
@@ -248,7 +248,7 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
   if (v.lazy) {
     // XFLOW_SEQ_RING: ring size override (tests exercise the flush with a tiny ring)
     const char* ring = getenv("XFLOW_SEQ_RING");
-    t->rows_cap = (ring && atoi(ring) >= 4) ? (size_t)atoi(ring) : ((size_t)1 << 20);
+    t->rows_cap = (ring && atoi(ring) >= 4 && atoi(ring) <= 65535) ? (size_t)atoi(ring) : (size_t)65535;  // tags are 16 bits
     XF_CUDA_TRY(cudaMalloc(&t->d_rows_by_seq, t->rows_cap * sizeof(uint32_t)));
     XF_CUDA_TRY(cudaMemsetAsync(t->d_rows_by_seq, 0, t->rows_cap * sizeof(uint32_t), t->stream));
     v.rows_by_seq = t->d_rows_by_seq;

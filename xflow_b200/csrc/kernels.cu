@@ -166,7 +166,7 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
         }
         if (SLOTG) h.g = -0.0;  // "untouched" marker for the next batch
         if (K > 0 && (part & 2)) h.flags |= XF_FLAG_V_READY;
-        xf_store_head(rowp, h);  // one full-sector store
+        xf_store_head_t(t, rowp, h);  // one full-sector store (lazy tables: in their own encoding)
       }
       if (lat) {
         const bool ready = (flags & XF_FLAG_V_READY) != 0;
@@ -439,10 +439,17 @@ __global__ void xf_k_import(XfTableView t, const uint32_t* __restrict__ slots, u
     uint8_t* rowp = xf_row(t, s);
     if (c == 0) {
       if (w) {
-        *reinterpret_cast<float2*>(rowp + XF_OFF_STATE) = make_float2(w[i], nw ? nw[i] : 0.f);
-        *reinterpret_cast<float*>(rowp + XF_OFF_STATE + 8) = zw ? zw[i] : 0.f;
-        *reinterpret_cast<unsigned long long*>(rowp + 8) = t.lazy ? 0ull : XF_NEG_ZERO_BITS64;
-        if (t.lazy) *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = 0u;  // no pending step
+        if (t.lazy) {
+          // lazy rows store (n, z) and derive the weight (FTRL), or store the weight (SGD): table.cuh
+          XfHead h;
+          h.key = *reinterpret_cast<const uint64_t*>(rowp);
+          h.w = w[i]; h.n = nw ? nw[i] : 0.f; h.z = zw ? zw[i] : 0.f; h.flags = 0u; h.g = 0.0;
+          xf_lazy_store(t, rowp, h, true);  // an imported weight need not be f(z, n): kept beside the state
+        } else {
+          *reinterpret_cast<float2*>(rowp + XF_OFF_STATE) = make_float2(w[i], nw ? nw[i] : 0.f);
+          *reinterpret_cast<float*>(rowp + XF_OFF_STATE + 8) = zw ? zw[i] : 0.f;
+          *reinterpret_cast<unsigned long long*>(rowp + 8) = XF_NEG_ZERO_BITS64;
+        }
       }
       if (v && K > 0) *reinterpret_cast<uint32_t*>(rowp + XF_OFF_FLAGS) = XF_FLAG_V_READY;
     } else if (v) {
@@ -616,9 +623,9 @@ __global__ void xf_k_flush_pending(XfTableView t) {
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < cap; r += (uint64_t)gridDim.x * blockDim.x) {
     uint8_t* rowp = xf_row(t, r);
     XfHead h = xf_load_head(rowp);
-    if (h.key == XF_EMPTY_KEY || !xf_has_pending(t, h)) continue;
+    if (h.key == XF_EMPTY_KEY || !xf_lazy_has_pending(h)) continue;
     xf_apply_pending(t, h);
-    xf_store_head(rowp, h);
+    xf_lazy_store(t, rowp, h);
   }
 }
 void xf_launch_flush_pending(const XfTableView& t, cudaStream_t st) {

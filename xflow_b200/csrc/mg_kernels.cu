@@ -315,13 +315,14 @@ __global__ void xf_k_bcast_rowv(const uint32_t* __restrict__ src, uint32_t n_wor
 // ---------------------------------------------------------------------------------------------------
 // owner: Push handler of ONE source rank, LR on a lazy table ("update on next touch", step_lazy.cu)
 // ---------------------------------------------------------------------------------------------------
-// Every token adds its row's residual to its key's sum g; the first token of this (step, source) that
-// touches a row "opens" it: folds the pending optimizer step of the row's previous (step, source) in and
-// stamps it with `seq` — one 128-bit CAS, xf_lazy_open in table.cuh.  The optimizer step of THIS push is
-// applied by the next touch (next opener, or on the fly by any reader) with divisor rows_by_seq[seq] = the
-// source's batch size: exactly one FTRL/SGD step per (source, key), sources in rank order because the S
-// launches are stream-ordered.  One token per lane, three row-touching instructions per token (load, CAS.128,
-// integer RED); lanes of a warp that hit the same row elect one of them.
+// The first token of this (step, source) that reaches a row folds the pending optimizer step of the row's
+// previous (step, source) in, stamps the row with `seq` and deposits its residual — one 128-bit CAS,
+// xf_lazy_deposit in table.cuh; later tokens of the same key add theirs with an integer RED.  The optimizer step
+// of THIS push is applied by the next touch (next opener, or on the fly by any reader) with divisor
+// rows_by_seq[seq] = the source's batch size: exactly one FTRL/SGD step per (source, key), sources in rank order
+// because the S launches are stream-ordered.  One token per lane; with the look at the row that this step's Pull
+// stashed (32 B per token, streaming) a token costs ONE row-touching instruction; lanes of a warp that hit the
+// same row elect one of them.
 __global__ void __launch_bounds__(256)
 xf_k_push_tokens_lr(XfTableView t, const uint32_t* __restrict__ slots, const uint32_t* __restrict__ in_rows,
                     const float* __restrict__ rowv, const uint32_t* __restrict__ meta_s, uint32_t cap, uint32_t seq,
@@ -346,42 +347,46 @@ xf_k_push_tokens_lr(XfTableView t, const uint32_t* __restrict__ slots, const uin
     }
     const bool valid = s != XF_NO_SLOT;
     uint8_t* rowp = xf_row(t, valid ? s : 0);
-    XfHead h;
-    h.flags = seq;
+    uint64_t q1 = 0ull, q2 = 0ull, q3 = (uint64_t)seq;  // invalid lanes: "open", nothing to do
     if (valid) {
       if (stash != nullptr) {
-        // the row as this step's Pull found it (coalesced, streaming) instead of a load of the row itself
+        // the row as this step's Pull found it (coalesced, streaming) instead of a load of the row
         const uint4 a = __ldcs(stash + 2 * (uint64_t)i), b = __ldcs(stash + 2 * (uint64_t)i + 1);
-        h.key = (uint64_t)a.x | ((uint64_t)a.y << 32);
-        h.g = __longlong_as_double((long long)((uint64_t)a.z | ((uint64_t)a.w << 32)));
-        h.w = __uint_as_float(b.x); h.n = __uint_as_float(b.y); h.z = __uint_as_float(b.z); h.flags = b.w;
+        q1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+        q2 = (uint64_t)b.x | ((uint64_t)b.y << 32);
+        q3 = (uint64_t)b.z | ((uint64_t)b.w << 32);
       } else {
-        h = xf_load_head(rowp);
+        const XfHead h = xf_load_head(rowp);
+        q1 = xf_raw_q1(h);
+        q2 = xf_raw_q2(h);
+        q3 = xf_raw_q3(h);
       }
     }
-    // tokens of this warp that hit the same row: the lowest lane opens it and adds the group's residuals
+    // tokens of this warp that hit the same row: the lowest lane deposits the group's residuals
     const unsigned grp = __match_any_sync(0xffffffffu, valid ? s : (0xFFFFFF00u | (uint32_t)lane));
     const bool lead = valid && lane == __ffs(grp) - 1;
-    unsigned long long fix = valid ? (unsigned long long)xf_fix_of(l) : 0ull;
+    long long fix = valid ? xf_fix_of(l) : 0ll;
     if (__any_sync(0xffffffffu, valid && __popc(grp) > 1)) {
-      unsigned long long sum = 0ull;
+      long long sum = 0ll;
       for (int b = 0; b < 32; ++b) {
-        const unsigned long long o = __shfl_sync(0xffffffffu, fix, b);
+        const long long o = __shfl_sync(0xffffffffu, fix, b);
         if ((grp >> b) & 1u) sum += o;
       }
       fix = sum;
     }
     if (lead) {
-      bool won = false, stale = false;
-      unsigned long long pend = 0ull;
-      xf_lazy_open(t, rowp, h, seq, won, pend, stash != nullptr ? &stale : nullptr);
+      uint64_t q2n;
+      bool stale = false;
+      xf_lazy_fold(t, q1, q2, q3, seq, q2n);
+      if (xf_lazy_deposit(t, rowp, q2, q3, q2n, seq, fix, stash != nullptr ? &stale : nullptr)) ++open_acc;
       if (stale) {
-        // an earlier source of this round (or an earlier launch) changed the row since the Pull: take a fresh look
-        h = xf_load_head(rowp);
-        xf_lazy_open(t, rowp, h, seq, won, pend);
+        // an earlier source of this round changed the row since the Pull: take a fresh look
+        const XfHead h = xf_load_head(rowp);
+        q2 = xf_raw_q2(h);
+        q3 = xf_raw_q3(h);
+        xf_lazy_fold(t, xf_raw_q1(h), q2, q3, seq, q2n);
+        if (xf_lazy_deposit(t, rowp, q2, q3, q2n, seq, fix)) ++open_acc;
       }
-      if (won) ++open_acc;
-      xf_lazy_add(rowp, fix - pend);
     }
   }
   if (open_acc) atomicAdd(&s_open, open_acc);

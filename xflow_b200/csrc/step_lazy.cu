@@ -8,26 +8,21 @@
 // Why: on a multi-GB table every row-touching instruction costs about the same (~28 ps of chip time: load,
 // store or atomic, hit or miss — tools/membench.cu, profiles/r02_membench.md), so the kernel's time is
 // (row-touching instructions per token) x 28 ps x tokens.  The eager pair (step + update) needs 4.3 per token,
-// round 1's lazy protocol (load, CAS on the tag, 256-bit store, RED) also 4.3 but in one launch; this one needs
-// 3.3: load (1.3 with the collision probes), ONE 128-bit CAS that claims and publishes, one integer RED.
-//
-// Protocol per row, batch b (tag = the row's flags word; xf_lazy_open in table.cuh):
-//   tag == b              open for b: w is current, g accumulates batch b.
-//   tag == p (p < b)      pending (p == 0: nothing pending): the token computes the row's new state from its
-//                         snapshot (FTRL/SGD step with g / rows[p]) and tries
-//                         CAS.128({w,n,z,tag}: snapshot -> {w',n',z', b}).  Exactly one token of the batch
-//                         succeeds; the others are handed the published state back by their failed CAS.
-//                         Nobody ever waits: there is no locked state.
-//   g                     64-bit fixed-point residual sum (scale 2^40).  The opener owes the row "- g_pending";
-//                         it pays in the same RED that adds its own residual after the row reduction
-//                         (integer adds commute exactly, so the order in which REDs land is irrelevant and the
-//                         result is bit-reproducible).
-// Inside a warp, tokens with the same slot elect one lane (__match_any_sync): one open and one RED of
+// round 1's lazy protocol (load, CAS on the tag, 256-bit store, RED) also 4.3 in one launch; this one 2.3:
+//   phase A  load the row (1.3 with the collision probes) and compute, in registers, the weight the batch
+//            pulls: the row's state with the pending step applied (pure function of what was loaded)
+//   phase B  after the row reduction, ONE 128-bit CAS per distinct key of the token group deposits the
+//            residual, publishes the new state and stamps the row for this batch (xf_lazy_deposit, table.cuh);
+//            a key that another token of the batch has opened already gets a 64-bit integer add instead.
+// No row is written before its residual is known, nobody waits, and because the residual sums are integers
+// the result does not depend on the order in which the atomics land (bit-reproducible).
+// Inside a warp, tokens with the same slot elect one lane (__match_any_sync): one deposit of
 // count x residual per distinct key of a 32-token group.
 //
 // Tried and measured on the 1e8-id table (profiles/r02_lazy_experiments.md): bucketised probing (collision
 // probes inside one 128-byte line: -3 %, kept), L2 prefetch by dedicated warps running ahead (+23 % time: the
-// prefetches are requests too, removed).
+// prefetches are requests too, removed), claim + publish in one CAS.128 with a separate RED (3.3 instructions
+// per token: 0.61 ms per headline batch against 0.72 ms for round 1's protocol).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -36,9 +31,9 @@
 #include "table.cuh"
 
 #define XF_NO_SLOT 0xFFFFFFFFu
-#define XF_LAZY_CACHED 2  // 64-token chunks whose leader slots stay in registers between the two phases
+#define XF_LAZY_CACHED 2  // 64-token chunks whose group leaders keep their look at the row for phase B
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uint64_t* __restrict__ keys,
                   const uint8_t* __restrict__ labels, int B, int mode, uint32_t seq, uint32_t* rows_by_seq,
                   float* __restrict__ loss_out, float* __restrict__ pctr_out, float* __restrict__ abs_loss_sum,
@@ -60,19 +55,19 @@ xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uin
     const uint32_t end = __ldg(row_ptr + row + 1);
     const int chunks = (int)((end - beg + 63u) >> 6);
     float wsum = 0.f;
-    // first XF_LAZY_CACHED chunks (rows <= 128 tokens), per half: the slot if this lane leads its group, the group
-    // size, and what the lane owes the row if it opened it
+    // first XF_LAZY_CACHED chunks (rows <= 128 tokens), per half: if this lane leads its group of equal slots,
+    // the slot, the group size, and the row's second half as it looked (old) and as it will be published (new)
     uint32_t lead_s[2 * XF_LAZY_CACHED];
     uint32_t cnt_c[XF_LAZY_CACHED];  // 8 bits per half
-    unsigned long long pend_c[2 * XF_LAZY_CACHED];
+    uint64_t q2_c[2 * XF_LAZY_CACHED], q3_c[2 * XF_LAZY_CACHED], q2n_c[2 * XF_LAZY_CACHED];
 #pragma unroll
     for (int c = 0; c < XF_LAZY_CACHED; ++c) {
       lead_s[2 * c] = lead_s[2 * c + 1] = XF_NO_SLOT;
-      pend_c[2 * c] = pend_c[2 * c + 1] = 0ull;
+      q2_c[2 * c] = q2_c[2 * c + 1] = q3_c[2 * c] = q3_c[2 * c + 1] = q2n_c[2 * c] = q2n_c[2 * c + 1] = 0ull;
       cnt_c[c] = 0;
     }
 
-    // ---------------- phase A: pull (and, in training, open) every token's row
+    // ---------------- phase A: pull every token's row; nothing is written
     for (int ch = 0; ch < chunks; ++ch) {
       const uint32_t j0 = beg + (uint32_t)ch * 64u + (uint32_t)lane;
       const uint32_t j1 = j0 + 32u;
@@ -83,48 +78,39 @@ xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uin
       XfHead h0, h1;
       h0.key = h1.key = XF_EMPTY_KEY;
       h0.flags = h1.flags = 0u;
+      h0.w = h0.n = h0.z = h1.w = h1.n = h1.z = 0.f;
+      h0.g = h1.g = 0.0;
       if (v0) h0 = xf_load_head(xf_row(t, p0));
       if (v1) h1 = xf_load_head(xf_row(t, p1));
       uint32_t s0 = XF_NO_SLOT, s1 = XF_NO_SLOT;
       if (v0) { const int64_t r = xf_probe_from<true>(t, k0, p0, h0); if (r >= 0) s0 = (uint32_t)r; }
       if (v1) { const int64_t r = xf_probe_from<true>(t, k1, p1, h1); if (r >= 0) s1 = (uint32_t)r; }
+      // the weight this batch pulls = the row with its pending step applied (computed, not stored)
+      const uint64_t a2 = xf_raw_q2(h0), a3 = xf_raw_q3(h0), b2 = xf_raw_q2(h1), b3 = xf_raw_q3(h1);
+      uint64_t a2n = a2, b2n = b2;
       float w0 = 0.f, w1 = 0.f;
-      uint32_t cnt0 = 0, cnt1 = 0;
-      unsigned long long pend0 = 0ull, pend1 = 0ull;
-      if (mode == 1) {
-        // forward only: apply a pending step on the fly, write nothing
-        if (s0 != XF_NO_SLOT) { xf_apply_pending(t, h0); w0 = h0.w; }
-        if (s1 != XF_NO_SLOT) { xf_apply_pending(t, h1); w1 = h1.w; }
-      } else {
-        // lanes with the same slot elect their lowest lane; invalid lanes get unique dummy values
-        const unsigned grp0 = __match_any_sync(0xffffffffu, (s0 != XF_NO_SLOT) ? s0 : (0xFFFFFF00u | (uint32_t)lane));
-        const unsigned grp1 = __match_any_sync(0xffffffffu, (s1 != XF_NO_SLOT) ? s1 : (0xFFFFFF00u | (uint32_t)lane));
-        const int lead0 = __ffs(grp0) - 1, lead1 = __ffs(grp1) - 1;
-        const bool L0 = s0 != XF_NO_SLOT && lane == lead0, L1 = s1 != XF_NO_SLOT && lane == lead1;
-        bool won0 = false, won1 = false;
-        if (L0) { w0 = xf_lazy_open(t, xf_row(t, s0), h0, seq, won0, pend0); cnt0 = (uint32_t)__popc(grp0); }
-        if (L1) { w1 = xf_lazy_open(t, xf_row(t, s1), h1, seq, won1, pend1); cnt1 = (uint32_t)__popc(grp1); }
-        open_acc += (won0 ? 1u : 0u) + (won1 ? 1u : 0u);
-        w0 = __shfl_sync(0xffffffffu, w0, lead0);
-        w1 = __shfl_sync(0xffffffffu, w1, lead1);
-        if (s0 == XF_NO_SLOT) w0 = 0.f;
-        if (s1 == XF_NO_SLOT) w1 = 0.f;
-        if (ch >= XF_LAZY_CACHED) {
-          // long rows (> 128 tokens): nothing is remembered for phase B, the opener pays its debt at once
-          if (won0) xf_lazy_add(xf_row(t, s0), 0ull - pend0);
-          if (won1) xf_lazy_add(xf_row(t, s1), 0ull - pend1);
-        }
-      }
+      if (s0 != XF_NO_SLOT) w0 = xf_lazy_fold(t, xf_raw_q1(h0), a2, a3, mode == 1 ? 0xFFFFFFFFu : seq, a2n);
+      if (s1 != XF_NO_SLOT) w1 = xf_lazy_fold(t, xf_raw_q1(h1), b2, b3, mode == 1 ? 0xFFFFFFFFu : seq, b2n);
       wsum += w0;
       wsum += w1;
+      if (mode == 1) continue;
+      // lanes with the same slot elect their lowest lane; invalid lanes get unique dummy values
+      const unsigned grp0 = __match_any_sync(0xffffffffu, (s0 != XF_NO_SLOT) ? s0 : (0xFFFFFF00u | (uint32_t)lane));
+      const unsigned grp1 = __match_any_sync(0xffffffffu, (s1 != XF_NO_SLOT) ? s1 : (0xFFFFFF00u | (uint32_t)lane));
+      const bool L0 = s0 != XF_NO_SLOT && lane == __ffs(grp0) - 1, L1 = s1 != XF_NO_SLOT && lane == __ffs(grp1) - 1;
+      if (ch >= XF_LAZY_CACHED) {
+        // long rows (> 128 tokens): nothing is remembered for phase B; open the row now with an empty deposit
+        if (L0 && xf_lazy_deposit(t, xf_row(t, s0), a2, a3, a2n, seq, 0ll)) ++open_acc;
+        if (L1 && xf_lazy_deposit(t, xf_row(t, s1), b2, b3, b2n, seq, 0ll)) ++open_acc;
+      }
 #pragma unroll
       for (int c = 0; c < XF_LAZY_CACHED; ++c)
         if (ch == c) {
-          lead_s[2 * c] = cnt0 ? s0 : XF_NO_SLOT;
-          lead_s[2 * c + 1] = cnt1 ? s1 : XF_NO_SLOT;
-          pend_c[2 * c] = pend0;
-          pend_c[2 * c + 1] = pend1;
-          cnt_c[c] = cnt0 | (cnt1 << 8);
+          lead_s[2 * c] = L0 ? s0 : XF_NO_SLOT;
+          lead_s[2 * c + 1] = L1 ? s1 : XF_NO_SLOT;
+          q2_c[2 * c] = a2; q3_c[2 * c] = a3; q2n_c[2 * c] = a2n;
+          q2_c[2 * c + 1] = b2; q3_c[2 * c + 1] = b3; q2n_c[2 * c + 1] = b2n;
+          cnt_c[c] = (L0 ? (uint32_t)__popc(grp0) : 0u) | ((L1 ? (uint32_t)__popc(grp1) : 0u) << 8);
         }
     }
 
@@ -137,19 +123,20 @@ xf_k_step_lr_lazy(XfTableView t, const uint32_t* __restrict__ row_ptr, const uin
     const float loss = __fsub_rn(pctr, (float)labels[row]);  // lr_worker.cc:141
     if (lane == 0 && loss_out) loss_out[row] = loss;
     abs_acc += fabsf(loss);
-    // ---------------- phase B: residual into the per-key sums (every row is open for `seq`); the rows
-    // are L2-resident right now, which is why this is not a separate kernel.  One lane per distinct slot of a
-    // group adds count x residual (minus what it owes as the row's opener): integer, exact.
-    const unsigned long long lf = (unsigned long long)xf_fix_of(loss);
+    // ---------------- phase B: one deposit per distinct key of a token group: count x residual, integer, exact
+    const long long lf = xf_fix_of(loss);
 #pragma unroll
     for (int c = 0; c < XF_LAZY_CACHED; ++c) {
-      if (lead_s[2 * c] != XF_NO_SLOT)
-        xf_lazy_add(xf_row(t, lead_s[2 * c]), lf * (unsigned long long)(cnt_c[c] & 0xFFu) - pend_c[2 * c]);
-      if (lead_s[2 * c + 1] != XF_NO_SLOT)
-        xf_lazy_add(xf_row(t, lead_s[2 * c + 1]), lf * (unsigned long long)(cnt_c[c] >> 8) - pend_c[2 * c + 1]);
+      if (lead_s[2 * c] != XF_NO_SLOT &&
+          xf_lazy_deposit(t, xf_row(t, lead_s[2 * c]), q2_c[2 * c], q3_c[2 * c], q2n_c[2 * c], seq, lf * (long long)(cnt_c[c] & 0xFFu)))
+        ++open_acc;
+      if (lead_s[2 * c + 1] != XF_NO_SLOT &&
+          xf_lazy_deposit(t, xf_row(t, lead_s[2 * c + 1]), q2_c[2 * c + 1], q3_c[2 * c + 1], q2n_c[2 * c + 1], seq,
+                          lf * (long long)(cnt_c[c] >> 8)))
+        ++open_acc;
     }
     for (int ch = XF_LAZY_CACHED; ch < chunks; ++ch) {
-      // long rows (> 128 tokens): slots are not cached; the rows were opened in phase A
+      // long rows (> 128 tokens): the rows were opened in phase A
       const uint32_t j0 = beg + (uint32_t)ch * 64u + (uint32_t)lane;
       const uint32_t j1 = j0 + 32u;
       XfHead h;

@@ -11,15 +11,26 @@
 //                                Double, so that the sum over a key's occurrences is exact to float
 //                                precision whatever order the L2 atomics land in (deterministic, and
 //                                more accurate than the reference's own sequential float sum).
-//                                LAZY tables (LR, "update on next touch"): the same 8 bytes hold the sum as a
-//                                64-bit FIXED-POINT integer (scale 2^40): integer adds are exactly associative
-//                                (deterministic) and exactly invertible, which the open protocol needs.
+//                                (LAZY tables keep their sum elsewhere, see below)
 //   byte 16  f32  w              app-0 weight                         (FTRLEntry_w::w / SGDEntry_w::w)
 //   byte 20  f32  n              FTRL accumulator of w (unused by SGD)
 //   byte 24  f32  z              FTRL accumulator of w (unused by SGD)
-//   byte 28  u32  flags          bit0 = latent block materialised (V_READY); lazy tables: the batch TAG.
-//                                {w, n, z, flags} are one aligned 16-byte word: lazy tables claim AND
-//                                publish a row with a single 128-bit compare-and-swap on it (step_lazy.cu)
+//   byte 28  u32  flags          bit0 = latent block materialised (V_READY)
+//   LAZY tables (LR, K == 0, "update on next touch", step_lazy.cu) use bytes 16..31 differently, so that ONE
+//   128-bit compare-and-swap on that aligned word can fold a pending optimizer step in, stamp the row for the
+//   current batch and deposit the first residual, all at once:
+//     byte 16  f32 n, byte 20 f32 z   (FTRL; the weight is not stored: w = f(z, n), the closed form the
+//                                      reference's handle evaluates after every push, ftrl.h:66-74)
+//              f32 w, byte 20 unused  (SGD)
+//     byte  8  f32 w_given, u32 check   a weight set from outside (xf_table_import) that is NOT f(z, n): it stands
+//                                      for w until the row's state changes (check = a digest of bytes 16..23;
+//                                      the reference would likewise use the stored w in its next step and then
+//                                      overwrite it with f(z', n'))
+//     byte 24  u64 { tag : 16 (low) | g : 48 (high) }   tag = the batch whose residual sum is pending in g
+//                                      (0: none); g = that sum as a signed FIXED-POINT integer (unit 2^-27):
+//                                      integer adds are exactly associative, so the result does not depend on
+//                                      the order the atomics land in (bit-reproducible), and an add of x << 16
+//                                      never disturbs the tag below it.
 //   ---- 32 B = one DRAM sector: an LR pull, gradient accumulate or update touches exactly one ----
 //   byte 32            f32 v[K]    app-1 latent row
 //   byte A             f64 L, f64 Aq   per-batch latent-gradient accumulators, A = round_up(32 + 4K, 16).
@@ -72,8 +83,9 @@ struct XfTableView {
   const uint32_t* rows_by_seq;
 };
 #define XF_TAG_LOCKED 0xFFFFFFFFu  // never a batch number (the sequence ring is far smaller)
-#define XF_FIX_SCALE 1099511627776.0        // 2^40: residual sums of lazy tables are integers of this unit
-#define XF_FIX_INV 9.094947017729282379e-13  // 2^-40
+#define XF_FIX_SCALE 134217728.0          // 2^27: residual sums of lazy tables are 48-bit integers of this unit
+#define XF_FIX_INV 7.450580596923828125e-9  // 2^-27  (|sum of a key's residuals in one batch| < 2^20)
+#define XF_TAG_MASK 0xFFFFull               // lazy rows: low 16 bits of the word at byte 24
 
 __host__ __device__ inline uint32_t xf_acc_off(int K) { return (32u + 4u * (uint32_t)K + 15u) & ~15u; }
 __host__ __device__ inline uint32_t xf_row_stride(int K, int opt) {
@@ -302,88 +314,131 @@ __device__ __forceinline__ float xf_div_rows(float g, double rows) {
   return (float)((double)g / rows);
 }
 
-// Lazy tables: the row as the reference's server would hold it — i.e. with the pending optimizer step
-// (the Push of the batch named by the tag) applied.  Pure function of the snapshot; writes nothing.
-__device__ __forceinline__ bool xf_has_pending(const XfTableView& t, const XfHead& h) {
-  return t.lazy && h.flags != 0u && h.flags != XF_TAG_LOCKED;
+// FTRL's weight as a function of its accumulators: the last lines of the reference's update (ftrl.h:66-74),
+// which it evaluates after every push — so (w, n, z) of a key always satisfy w == xf_ftrl_w(z, n).
+__device__ __forceinline__ float xf_ftrl_w(const XfTableView& t, float z, float n) {
+  if (fabsf(z) <= t.lambda1) return 0.0f;
+  float tmpr = 0.0f;
+  if (z > 0.0f) tmpr = __fsub_rn(z, t.lambda1);
+  if (z < 0.0f) tmpr = __fadd_rn(z, t.lambda1);
+  const float tmpl = -__fadd_rn(__fdiv_rn(__fadd_rn(t.beta, __fsqrt_rn(n)), t.alpha), t.lambda2);
+  return __fdiv_rn(tmpr, tmpl);
 }
-// lazy tables: the residual sum of a row (fixed point, see XF_FIX_SCALE) and a residual in that unit
-__device__ __forceinline__ long long xf_head_gfix(const XfHead& h) { return __double_as_longlong(h.g); }
 __device__ __forceinline__ long long xf_fix_of(float residual) { return __double2ll_rn((double)residual * XF_FIX_SCALE); }
-// the pending optimizer step of a lazy row: gradient = (float)(residual sum) / rows   (lr_worker.cc:116-118)
-__device__ __forceinline__ void xf_fold_pending(const XfTableView& t, long long gfix, uint32_t rows, float& w, float& n,
-                                                float& z) {
-  // the residual sum is rounded to float once (push_gradient is a float vector), then divided in double
-  const float g = xf_div_rows_plain((float)((double)gfix * XF_FIX_INV), (double)rows);
-  xf_opt_coord(t, g, w, n, z);
+
+// ---- lazy rows: the raw second half {q2 = bytes 16..23, q3 = bytes 24..31} of a row loaded with xf_load_head
+__device__ __forceinline__ uint64_t xf_raw_q2(const XfHead& h) {
+  return (uint64_t)__float_as_uint(h.w) | ((uint64_t)__float_as_uint(h.n) << 32);
 }
+__device__ __forceinline__ uint64_t xf_raw_q3(const XfHead& h) {
+  return (uint64_t)__float_as_uint(h.z) | ((uint64_t)h.flags << 32);
+}
+__device__ __forceinline__ uint64_t xf_raw_q1(const XfHead& h) { return (uint64_t)__double_as_longlong(h.g); }
+// digest of a lazy row's state word that validates an imported weight kept in bytes 8..15 (never 0 for q2 == 0)
+__device__ __forceinline__ uint32_t xf_lazy_check(uint64_t q2) { return (uint32_t)q2 ^ (uint32_t)(q2 >> 32) ^ 0xA5A5A5A5u; }
+// What batch `seq` pulls from a lazy row whose second half is (q2, q3): the weight with the pending optimizer
+// step (the Push of the batch named by the tag, gradient = (float)(residual sum) / rows, lr_worker.cc:116-118)
+// applied.  q2_new = the first word the row gets when it is opened (its state after that step).  Pure.
+__device__ __forceinline__ float xf_lazy_fold(const XfTableView& t, uint64_t q1, uint64_t q2, uint64_t q3, uint32_t seq,
+                                              uint64_t& q2_new) {
+  const uint32_t tag = (uint32_t)(q3 & XF_TAG_MASK);
+  const bool pending = tag != 0u && tag != seq;
+  float g = 0.f;
+  if (pending) {
+    const long long gfix = (long long)q3 >> 16;
+    // the residual sum is rounded to float once (push_gradient is a float vector), then divided in double
+    g = xf_div_rows_plain((float)((double)gfix * XF_FIX_INV), (double)__ldg(t.rows_by_seq + tag));
+  }
+  const float a = __uint_as_float((uint32_t)q2), b = __uint_as_float((uint32_t)(q2 >> 32));
+  if (t.opt == XF_OPT_FTRL) {
+    float n = a, z = b;
+    float w = ((uint32_t)(q1 >> 32) == xf_lazy_check(q2)) ? __uint_as_float((uint32_t)q1) : xf_ftrl_w(t, z, n);
+    if (pending) xf_ftrl_coord(t, g, w, n, z);
+    q2_new = (uint64_t)__float_as_uint(n) | ((uint64_t)__float_as_uint(z) << 32);
+    return w;
+  }
+  float w = a;
+  if (pending) xf_sgd_coord(t, g, w);
+  q2_new = (uint64_t)__float_as_uint(w);
+  return w;
+}
+// A raw-loaded head of a lazy row -> the row as the reference's server would hold it right now (pending step
+// applied): canonical fields w, n, z; flags = 0; g = 0.  Every reader outside the step kernels goes through this.
 __device__ __forceinline__ void xf_apply_pending(const XfTableView& t, XfHead& h) {
-  if (!xf_has_pending(t, h)) return;
-  xf_fold_pending(t, xf_head_gfix(h), __ldg(t.rows_by_seq + h.flags), h.w, h.n, h.z);
+  if (!t.lazy) return;
+  uint64_t q2n;
+  const float w = xf_lazy_fold(t, xf_raw_q1(h), xf_raw_q2(h), xf_raw_q3(h), 0xFFFFFFFFu, q2n);
+  h.w = w;
+  if (t.opt == XF_OPT_FTRL) {
+    h.n = __uint_as_float((uint32_t)q2n);
+    h.z = __uint_as_float((uint32_t)(q2n >> 32));
+  } else {
+    h.n = 0.f;
+    h.z = 0.f;
+  }
   h.flags = 0u;
-  h.g = 0.0;  // all-zero bits: also the fixed-point zero
+  h.g = 0.0;
+}
+__device__ __forceinline__ bool xf_lazy_has_pending(const XfHead& raw) { return (xf_raw_q3(raw) & XF_TAG_MASK) != 0ull; }
+// store a canonical head (no pending step) into a lazy row.  keep_w: the weight was set from outside and need
+// not be f(z, n) (xf_table_import): keep it beside the state
+__device__ __forceinline__ void xf_lazy_store(const XfTableView& t, uint8_t* rowp, const XfHead& h, bool keep_w = false) {
+  const bool ftrl = t.opt == XF_OPT_FTRL;
+  const uint64_t q2 = ftrl ? ((uint64_t)__float_as_uint(h.n) | ((uint64_t)__float_as_uint(h.z) << 32))
+                           : (uint64_t)__float_as_uint(h.w);
+  uint64_t q1 = 0ull;
+  if (keep_w && ftrl && __float_as_uint(h.w) != __float_as_uint(xf_ftrl_w(t, h.z, h.n)))
+    q1 = (uint64_t)__float_as_uint(h.w) | ((uint64_t)xf_lazy_check(q2) << 32);
+  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(rowp), "l"(h.key), "l"(q1), "l"(q2), "l"(0ull) : "memory");
+}
+// store a canonical head into a row of either kind
+__device__ __forceinline__ void xf_store_head_t(const XfTableView& t, uint8_t* rowp, const XfHead& h) {
+  if (t.lazy) xf_lazy_store(t, rowp, h);
+  else xf_store_head(rowp, h);
 }
 
-// ---- lazy tables: claim AND publish a row with ONE 128-bit compare-and-swap on {w, n, z, tag} -------------
+// ---- lazy tables: fold + open + deposit with ONE 128-bit compare-and-swap ------------------------------------
 // Measured on B200 (tools/membench.cu, profiles/r02_membench.md): on a multi-GB table every instruction that
-// touches a random row costs about the same whatever it is — load, store, CAS or RED, hit or miss (the
-// translation / request path saturates near 36 G requests/s) — so the number of row-touching instructions
-// per token is what sets the speed of these kernels.  The round-1 protocol used four (load, CAS on the tag,
-// 256-bit store, RED); this one uses three (load, CAS.128, RED) and has no LOCKED state to poll.
-struct XfState {
-  float w, n, z;
-  uint32_t flags;
-};
-__device__ __forceinline__ bool xf_cas_state(uint8_t* rowp, const XfState& expect, const XfState& desired, XfState& found) {
-  const uint64_t e0 = (uint64_t)__float_as_uint(expect.w) | ((uint64_t)__float_as_uint(expect.n) << 32);
-  const uint64_t e1 = (uint64_t)__float_as_uint(expect.z) | ((uint64_t)expect.flags << 32);
-  const uint64_t d0 = (uint64_t)__float_as_uint(desired.w) | ((uint64_t)__float_as_uint(desired.n) << 32);
-  const uint64_t d1 = (uint64_t)__float_as_uint(desired.z) | ((uint64_t)desired.flags << 32);
-  uint64_t o0, o1;
+// touches a random row costs about the same whatever it is — load, store, CAS or RED, hit or miss (the request
+// path saturates near 36 G requests/s) — so the number of row-touching instructions per token is what sets the
+// speed of these kernels.  Round 1's protocol needed four (load, CAS on the tag, 256-bit store, RED).  Here a
+// token needs two: the load, and this deposit — which for the FIRST token of a batch on a row is a CAS.128 of
+// {state, tag, g}: (pending state, p, sum_p) -> (state after the step of p, seq, its own residual), and for a
+// later token of the same batch (duplicate keys) a 64-bit integer add into g.  Nobody ever waits or polls.
+__device__ __forceinline__ bool xf_cas128(uint8_t* addr, uint64_t e0, uint64_t e1, uint64_t d0, uint64_t d1, uint64_t& o0,
+                                          uint64_t& o1) {
   asm volatile(
       "{\n .reg .b128 cmp, swp, old;\n mov.b128 cmp, {%2, %3};\n mov.b128 swp, {%4, %5};\n"
       " atom.global.cas.b128 old, [%6], cmp, swp;\n mov.b128 {%0, %1}, old;\n}"
       : "=l"(o0), "=l"(o1)
-      : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "l"(rowp + XF_OFF_STATE)
+      : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "l"(addr)
       : "memory");
-  found.w = __uint_as_float((uint32_t)o0);
-  found.n = __uint_as_float((uint32_t)(o0 >> 32));
-  found.z = __uint_as_float((uint32_t)o1);
-  found.flags = (uint32_t)(o1 >> 32);
   return o0 == e0 && o1 == e1;
 }
-// "Open" a row for batch `seq` from the snapshot `h` a token has loaded: the first token of the batch that gets
-// there folds the pending optimizer step of the row's previous batch in and stamps the row with `seq`, all in the
-// one CAS; everybody else finds (or is handed back by the failed CAS) the published weight.  Returns the weight
-// the batch pulls.  `won` = this token opened the row; it then OWES the row the removal of the consumed residual
-// sum: `pend` = the raw 64 bits of g in its snapshot, to be subtracted in the same RED that adds the token's own
-// residual (integer arithmetic mod 2^64: exact, whatever lands in between).  g of the snapshot is final when the
-// CAS succeeds: residuals of batch `seq` are only added to rows that were seen open, i.e. after this CAS.
-// `stale` (optional): the caller's snapshot may be OLDER than this batch (the sharded owner keeps the snapshot its
-// Pull took, mg_kernels.cu); a CAS that fails against a row which is not open for `seq` then reports *stale = true
-// instead of an error, and the caller reloads the row and tries again.
-__device__ __forceinline__ float xf_lazy_open(const XfTableView& t, uint8_t* rowp, const XfHead& h, uint32_t seq,
-                                              bool& won, unsigned long long& pend, bool* stale = nullptr) {
-  won = false;
-  pend = 0ull;
-  if (stale) *stale = false;
-  if (h.flags == seq) return h.w;
-  XfState e{h.w, h.n, h.z, h.flags}, d = e, f;
-  if (h.flags != 0u) xf_fold_pending(t, xf_head_gfix(h), __ldg(t.rows_by_seq + h.flags), d.w, d.n, d.z);
-  d.flags = seq;
-  if (xf_cas_state(rowp, e, d, f)) {
-    won = true;
-    pend = (unsigned long long)__double_as_longlong(h.g);
-    return d.w;
-  }
-  if (f.flags != seq) {
-    if (stale) *stale = true;
-    else *t.error = 2;  // inside a batch a row only ever goes from "pending" to "open for seq"
-  }
-  return f.w;
+__device__ __forceinline__ void xf_lazy_add(uint8_t* rowp, long long fix) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(rowp + 24), (unsigned long long)fix << 16);  // never carries into the tag
 }
-__device__ __forceinline__ void xf_lazy_add(uint8_t* rowp, unsigned long long fix) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(rowp + 8), fix);
+// Deposit `fix` units of residual of batch `seq` into the row whose second half was (q2, q3) when the caller
+// looked; q2_new from xf_lazy_fold.  Returns true when this call opened the row (= the key's first token of the
+// batch: the unique-key count).  *stale (optional): the caller's look may be OLDER than this batch (the sharded
+// owner works from the look its Pull took); a row that meanwhile moved on to another batch is then reported
+// instead of flagged as an error, and the caller looks again.
+__device__ __forceinline__ bool xf_lazy_deposit(const XfTableView& t, uint8_t* rowp, uint64_t q2, uint64_t q3, uint64_t q2_new,
+                                                uint32_t seq, long long fix, bool* stale = nullptr) {
+  if (stale) *stale = false;
+  if ((uint32_t)(q3 & XF_TAG_MASK) == seq) {  // already open for this batch
+    xf_lazy_add(rowp, fix);
+    return false;
+  }
+  uint64_t o2, o3;
+  if (xf_cas128(rowp + XF_OFF_STATE, q2, q3, q2_new, ((unsigned long long)fix << 16) | (uint64_t)seq, o2, o3)) return true;
+  if ((uint32_t)(o3 & XF_TAG_MASK) == seq) {  // another token of this batch was first
+    xf_lazy_add(rowp, fix);
+    return false;
+  }
+  if (stale) *stale = true;
+  else *t.error = 2;  // inside a batch a row only ever goes from "pending" to "open for seq"
+  return false;
 }
 
 __device__ __forceinline__ float xf_warp_sum(float v) {

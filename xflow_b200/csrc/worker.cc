@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 #include <iostream>
 #include <mutex>
@@ -191,6 +192,9 @@ void WorkerBase::update(int start, int end) {
 // a well-formed text block of `bytes` bytes holds at most bytes/8 rows ("0\ta:b:c\n") and bytes/6 tokens
 // ("a:b:c ")
 void WorkerBase::ensure_trainer_for_block(uint64_t bytes) {
+  // sharded: one trainer for the whole run (its exchange buffers are mapped by the peers): big enough for the
+  // training blocks AND the prediction blocks
+  if (comm_) bytes = std::max<uint64_t>(bytes, (uint64_t)std::max(block_size, test_block_size) << 20);
   ensure_trainer((uint32_t)(bytes / 8 + 2), (uint32_t)(bytes / 6 + 2));
 }
 
