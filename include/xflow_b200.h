@@ -226,6 +226,26 @@ XF_DLL int xf_auc_logloss(const int32_t* labels, const float* pctr, uint64_t n, 
  * likelihood, out[1] = AUC with ties counted 1/2, out[2]=positives out[3]=negatives */
 XF_DLL int xf_auc_logloss_exact(const int32_t* labels, const float* pctr, uint64_t n, double out[4]);
 
+/* The metric on the DEVICE (csrc/metric.cu): predictions and labels of every forward block are appended to a
+ * device buffer, xf_metric_finish sorts them there (radix sort, stable) and reduces:
+ *   out[0] the reference's logloss (base 2, not negated; double accumulator)   out[1] the reference's AUC (64-bit
+ *   integer rank sum instead of the float `area` that stops counting at 2^24)  out[2] positives  out[3] negatives
+ *   out[4] mean negative natural-log likelihood   out[5] AUC with ties counted 1/2          (base.h:84-110) */
+typedef struct xf_metric xf_metric;
+XF_DLL int xf_metric_create(xf_metric** out, int device);
+XF_DLL int xf_metric_destroy(xf_metric* m);
+XF_DLL int xf_metric_reset(xf_metric* m);
+/* append n predictions / 0-1 labels living in device memory (copies run on `cuda_stream`, no sync) */
+XF_DLL int xf_metric_add_device(xf_metric* m, const float* d_pctr, const uint8_t* d_labels, uint64_t n, void* cuda_stream);
+XF_DLL int xf_metric_finish(xf_metric* m, void* cuda_stream, double out[6]);
+XF_DLL int xf_auc_logloss_device(const float* d_pctr, const uint8_t* d_labels, uint64_t n, int device, void* cuda_stream,
+                                 double out[6]);
+/* forward pass over rows [row_start, row_end) of the current ingested block, appended to `m` without leaving the
+ * device (asynchronous).  pctr_out / labels_out (optional host arrays of rows elements): the same values for a
+ * caller that also writes them out; the call then waits for them. */
+XF_DLL int xf_trainer_predict_ingested_metric(xf_trainer* tr, uint32_t row_start, uint32_t row_end, xf_metric* m,
+                                              float* pctr_out, uint8_t* labels_out);
+
 /* ------------------------------------------------------------------------------------------------
  * 4. Host ingest
  * ---------------------------------------------------------------------------------------------- */

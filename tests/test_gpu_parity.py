@@ -447,3 +447,47 @@ def test_checkpoint_rejects_corrupt_files(tmp_path):
             g2.load(path)
     with pytest.raises(api.XflowError):
         gt.save(str(tmp_path / "no_such_dir" / "x.bin"))
+
+
+def test_device_metric_matches_host_metric():
+    """metric.cu: sort + rank sums on the device against the host implementations of Base::calculate_auc
+    (base.h:84-110, float quirks) and of the exact metric; many ties, both classes, and a one-class case."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(5)
+    n = 50000
+    p = np.round(rng.random(n), 3).astype(np.float32).clip(1e-4, 1 - 1e-4)   # 1000 distinct values: heavy ties
+    y = (rng.random(n) < p).astype(np.uint8)
+    lib = api.lib()
+    m = C.c_void_p()
+    assert lib.xf_metric_create(C.byref(m), 0) == 0
+    d_p, d_y = torch.from_numpy(p).cuda(), torch.from_numpy(y).cuda()
+    torch.cuda.synchronize()
+    for lo, hi in ((0, 17000), (17000, 17001), (17001, n)):                   # appended block by block
+        assert lib.xf_metric_add_device(m, C.c_void_p(d_p.data_ptr() + 4 * lo), C.c_void_p(d_y.data_ptr() + lo), hi - lo, None) == 0
+    out = (C.c_double * 6)()
+    assert lib.xf_metric_finish(m, None, out) == 0, lib.xf_last_error()
+    ex = api.auc_logloss_exact(y.astype(np.int32), p)
+    assert out[2] == ex["positives"] and out[3] == ex["negatives"]
+    assert abs(out[4] - ex["logloss"]) <= 1e-9 * abs(ex["logloss"])
+    assert abs(out[5] - ex["auc"]) <= 1e-12
+    # the reference-style numbers: same definitions, float accumulators on the host; ties make the reference's AUC
+    # depend on its sort's tie order, so compare on data without ties across classes
+    q = (np.arange(n, dtype=np.float32) + 1) / (n + 1)
+    rng.shuffle(q)
+    d_q = torch.from_numpy(q).cuda()
+    torch.cuda.synchronize()
+    assert lib.xf_metric_reset(m) == 0
+    assert lib.xf_metric_add_device(m, C.c_void_p(d_q.data_ptr()), C.c_void_p(d_y.data_ptr()), n, None) == 0
+    assert lib.xf_metric_finish(m, None, out) == 0
+    ref = api.auc_logloss(y.astype(np.int32), q)
+    assert abs(out[0] - ref["logloss"]) <= 2e-5 * abs(ref["logloss"])      # the host accumulates in a float
+    assert abs(out[1] - ref["auc"]) <= 2e-5
+    # one class only: no AUC
+    assert lib.xf_metric_reset(m) == 0
+    d_z = torch.zeros(n, dtype=torch.uint8).cuda()
+    torch.cuda.synchronize()
+    assert lib.xf_metric_add_device(m, C.c_void_p(d_q.data_ptr()), C.c_void_p(d_z.data_ptr()), n, None) == 0
+    assert lib.xf_metric_finish(m, None, out) == 0
+    assert out[2] == 0 and np.isnan(out[1]) and np.isnan(out[5])
+    lib.xf_metric_destroy(m)

@@ -89,6 +89,13 @@ SIGNATURES = {
     "xf_host_alloc": (_i, [_vp, _u64]),
     "xf_host_free": (_i, [_vp]),
     "xf_auc_logloss": (_i, [_vp, _vp, _u64, _vp]),
+    "xf_metric_create": (_i, [_vp, _i]),
+    "xf_metric_destroy": (_i, [_vp]),
+    "xf_metric_reset": (_i, [_vp]),
+    "xf_metric_add_device": (_i, [_vp, _vp, _vp, _u64, _vp]),
+    "xf_metric_finish": (_i, [_vp, _vp, _vp]),
+    "xf_auc_logloss_device": (_i, [_vp, _vp, _u64, _i, _vp, _vp]),
+    "xf_trainer_predict_ingested_metric": (_i, [_vp, _u32, _u32, _vp, _vp, _vp]),
     "xf_hash_bytes": (_u64, [C.c_char_p, _u64]),
     "xf_hash_decimal_ids": (_i, [_vp, _u64, _vp]),
     "xf_loader_open": (_i, [_vp, C.c_char_p, _u64]),

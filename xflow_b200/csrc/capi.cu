@@ -209,11 +209,12 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
     return XF_ERR_ARG;
   }
   XF_CUDA_TRY(cudaSetDevice(cfg->device));
-  // L2 fetch granularity = one probing bucket (LR: 4 rows = 128 B, so that the further probes of a bucket
-  // hit the line the first probe fetched; FM: head + latent row of a key are contiguous, 96+ B).  A hint —
-  // the driver may ignore it; measured with ncu dram__bytes_read.  XFLOW_L2_FETCH = 32 / 64 / 128 overrides.
+  // L2 fetch granularity: one sector.  The table is read and written one random 32-byte row at a time; with the
+  // default (64 B) or a whole 128-byte bucket per miss the DRAM read traffic doubles / quadruples (ncu, headline
+  // LR batch: 340 MB at 32 B, 932 MB at 128 B) for a 3 % shorter kernel — the kernels are bound by the request
+  // rate, not by DRAM.  A hint: the driver may ignore it.  XFLOW_L2_FETCH = 32 / 64 / 128.
   {
-    int fetch = 128;
+    int fetch = 32;
     const char* fe = getenv("XFLOW_L2_FETCH");
     if (fe && (atoi(fe) == 32 || atoi(fe) == 64 || atoi(fe) == 128)) fetch = atoi(fe);
     if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch) != cudaSuccess) cudaGetLastError();
@@ -1105,6 +1106,13 @@ XF_DLL int xf_trainer_ingested_export(xf_trainer* tr, uint32_t* row_ptr_out, uin
   if (labels_out && tr->ing_rows)
     XF_CUDA_TRY(cudaMemcpy(labels_out, g.labels.p, (size_t)tr->ing_rows, cudaMemcpyDeviceToHost));
   return XF_OK;
+}
+
+// forward pass over a row range of the current ingested block; predictions stay in tr->pctr (metric.cu)
+int xf_trainer_forward_ingested(xf_trainer* tr, uint32_t row_start, uint32_t row_end) {
+  xf_trainer::IngestSet& g = tr->ing[tr->ing_cur];
+  return xf_step_device_impl(tr, g.row_ptr.as<uint32_t>() + row_start, g.keys.as<uint64_t>(),
+                             g.labels.as<uint8_t>() + row_start, row_end - row_start, tr->ing_nnz, 1, nullptr);
 }
 
 // Forward pass over a row range of the current block.  Asynchronous when pinned result buffers are given

@@ -362,6 +362,10 @@ void WorkerBase::predict(int rank_arg, int block) {
   if (!host_parse) ensure_trainer_for_block(block_bytes);
   std::vector<float> pctr_buf;
   std::vector<uint8_t> label_buf;
+  // the metric is computed on the device (sort + reductions, metric.cu); the predictions come back only because
+  // the reference writes every one of them to pred_<rank>_<block>.txt
+  xf_metric* metric = nullptr;
+  if (!host_parse) must(xf_metric_create(&metric, Server::Get()->device()), "xf_metric_create");
   if (!host_parse) {
     if (feeding) open_loader(test_data_path, block_bytes);
     else open_loader("/dev/null", block_bytes);  // nothing to feed: every block is empty
@@ -370,9 +374,10 @@ void WorkerBase::predict(int rank_arg, int block) {
       pctr_buf.resize(thread_size + 1);
       label_buf.resize(thread_size + 1);
       for (uint32_t i = 0; i < (uint32_t)core_num; ++i) {
-        must(xf_trainer_predict_ingested(trainer_, i * thread_size, (i + 1) * thread_size, pctr_buf.data(),
-                                         label_buf.data()),
-             "xf_trainer_predict_ingested");
+        must(xf_trainer_predict_ingested_metric(trainer_, i * thread_size, (i + 1) * thread_size, metric,
+                                                feeding ? pctr_buf.data() : nullptr, feeding ? label_buf.data() : nullptr),
+             "xf_trainer_predict_ingested_metric");
+        if (!feeding) continue;
         for (uint32_t r = 0; r < thread_size; ++r) {
           auc_key ak;
           ak.label = label_buf[r];
@@ -396,7 +401,26 @@ void WorkerBase::predict(int rank_arg, int block) {
   cur_row_ptr_ = nullptr;
   cur_keys_ = nullptr;
   cur_labels_ = nullptr;
+  double dm[6] = {0, 0, 0, 0, 0, 0};
+  if (metric) {
+    if (feeding) must(xf_metric_finish(metric, nullptr, dm), "xf_metric_finish");
+    xf_metric_destroy(metric);
+  }
   if (!feeding) return;
+  if (metric && env_int("XFLOW_HOST_METRIC", 0) == 0) {
+    // Base::calculate_auc's printout (base.h:101-109) from the device-side metric
+    last_logloss = dm[0];
+    last_auc = dm[1];
+    std::cout << "logloss: " << (float)dm[0] << "\t";
+    if (dm[2] == 0 || dm[3] == 0) {
+      std::cout << "tp_n = " << (int)dm[2] << std::endl;
+    } else {
+      std::cout << "auc = " << (float)dm[1] << "\ttp = " << (int)dm[2] << " fp = " << (size_t)dm[3] << std::endl;
+    }
+    if (env_int("XFLOW_EXACT_METRIC", 0))
+      std::cout << "exact: logloss(ln) = " << dm[4] << "\tauc = " << dm[5] << std::endl;
+    return;
+  }
 
   // Base::calculate_auc (base.h:84-110), same printout
   std::vector<int32_t> labels(test_auc_vec.size());
