@@ -41,7 +41,8 @@ enum {
   XF_ERR_STATE = -6
 };
 
-enum { XF_MODEL_LR = 0, XF_MODEL_FM = 1 };            /* main.cc:26-39: '0' = LR, '1' = FM */
+enum { XF_MODEL_LR = 0, XF_MODEL_FM = 1,              /* main.cc:26-39: '0' = LR, '1' = FM */
+       XF_MODEL_FM_CANONICAL = 2 };                   /* NOT the reference's model: the textbook FM, see below */
 enum { XF_OPTIMIZER_FTRL = 0, XF_OPTIMIZER_SGD = 1 }; /* server.h:24-29 (comment toggle in the reference) */
 enum {
   XF_VINIT_DEFAULT = 0,  /* FTRL: N(0,1)*1e-2 (ftrl.h:114-120, counter-based here); SGD: 0.001 (sgd.h:68-70) */
@@ -73,6 +74,7 @@ typedef struct xf_table_config {
   uint64_t capacity;     /* initial slot count (rounded up to a power of two); 0 = 1<<20.  Grows on demand. */
   int shard_index;       /* this table owns keys of shard_index out of num_shards (postoffice.cc:134-143) */
   int num_shards;        /* 1 = whole key space */
+  int canonical_fm;      /* 1: rows carry the accumulators of XF_MODEL_FM_CANONICAL (latent_dim in {4,8,16,32,64,128}) */
 } xf_table_config;
 
 /* fills *cfg with the reference's compile-time defaults (ftrl.h:15-20, sgd.h:16) */
@@ -164,6 +166,17 @@ XF_DLL int xf_trainer_step_device(xf_trainer* tr, const uint32_t* d_row_ptr, con
 /* replaces: calculate_pctr (lr_worker.cc:25-71, fm_worker.cc:25-96): forward only, pctr_out[rows] host */
 XF_DLL int xf_trainer_predict_host(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys, uint32_t rows,
                                    uint32_t nnz, float* pctr_out);
+/* The textbook factorisation machine with feature VALUES (the reference ignores `val` and collapses
+ * the interaction over k, fm_worker.cc:177-196 — parity mode = XF_MODEL_FM):
+ *     y = sum_i w_i x_i + 1/2 sum_k [ (sum_i v_ik x_i)^2 - sum_i (v_ik x_i)^2 ],   p = sigmoid(y)
+ *     dL/dw_i = (p - label) x_i ,  dL/dv_ik = (p - label) x_i (S_k - v_ik x_i) ,  gradients / rows, one FTRL / SGD step
+ * vals[nnz] are the tokens' values (NULL: all 1).  Needs a table created with canonical_fm = 1; single GPU. */
+XF_DLL int xf_trainer_step_host_values(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys, const float* vals,
+                                       const uint8_t* labels, uint32_t rows, uint32_t nnz, float* mean_abs_loss);
+XF_DLL int xf_trainer_step_device_values(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys,
+                                         const float* d_vals, const uint8_t* d_labels, uint32_t rows, uint32_t nnz);
+XF_DLL int xf_trainer_predict_host_values(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys, const float* vals,
+                                          uint32_t rows, uint32_t nnz, float* pctr_out);
 /* the one-off "init push" of key 0 with zero gradient (lr_worker.cc:180-182, fm_worker.cc:248-252) */
 XF_DLL int xf_trainer_init_push(xf_trainer* tr);
 /* residuals (pctr - label) of the last step; needs keep_loss = 1 */

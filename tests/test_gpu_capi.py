@@ -163,3 +163,25 @@ def test_rank_without_world_is_refused(tmp_path):
     env.pop("XFLOW_WORLD", None); env.pop("WORLD_SIZE", None)
     r = subprocess.run([exe, TRAIN, TEST, "0", "1"], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "XFLOW_WORLD" in (r.stdout + r.stderr)
+
+
+def test_cli_device_metric_prints_the_same_numbers(tmp_path):
+    """XFLOW_DEVICE_METRIC=1: logloss / AUC computed on the device (metric.cu) — the same quantities as the reference's
+    Base::calculate_auc without its float accumulators; on the bundled shard they agree with the reference's printout
+    to the tolerance its own float arithmetic leaves (ties between rows of different labels are the only other
+    difference: the reference orders them by std::sort, the device keeps input order)."""
+    exe = os.path.join(ROOT, "xflow_b200", "bin", "xflow_lr")
+    outs = {}
+    for dev in ("0", "1"):
+        d = tmp_path / ("m" + dev)
+        d.mkdir()
+        env = dict(os.environ, XFLOW_OPTIMIZER="ftrl", XFLOW_DEVICE_METRIC=dev, XFLOW_EXACT_METRIC="1")
+        r = subprocess.run([exe, TRAIN, TEST, "0", "10"], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[dev] = (_parse(r.stdout), re.search(r"exact: logloss\(ln\) = (\S+)\s+auc = (\S+)", r.stdout))
+    (ll0, auc0, tp0, fp0), ex0 = outs["0"]
+    (ll1, auc1, tp1, fp1), ex1 = outs["1"]
+    assert (tp0, fp0) == (tp1, fp1)
+    assert abs(ll0 - ll1) <= 2e-5 * abs(ll0) + 1e-6
+    assert abs(auc0 - auc1) <= 5e-3            # tie order only
+    assert abs(float(ex0.group(1)) - float(ex1.group(1))) <= 1e-6 and abs(float(ex0.group(2)) - float(ex1.group(2))) <= 1e-9

@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libxflow_b200.so")
 
-MODEL_LR, MODEL_FM = 0, 1
+MODEL_LR, MODEL_FM, MODEL_FM_CANONICAL = 0, 1, 2
 OPT_FTRL, OPT_SGD = 0, 1
 VINIT_DEFAULT, VINIT_COUNTER, VINIT_ZERO = 0, 1, 3
 COMM_ID_BYTES = 128
@@ -27,7 +27,7 @@ class TableConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("latent_dim", C.c_int), ("optimizer", C.c_int), ("alpha", C.c_float),
                 ("beta", C.c_float), ("lambda1", C.c_float), ("lambda2", C.c_float),
                 ("learning_rate", C.c_float), ("v_init", C.c_int), ("seed", C.c_uint64),
-                ("capacity", C.c_uint64), ("shard_index", C.c_int), ("num_shards", C.c_int)]
+                ("capacity", C.c_uint64), ("shard_index", C.c_int), ("num_shards", C.c_int), ("canonical_fm", C.c_int)]
 
 
 class TrainerConfig(C.Structure):
@@ -66,6 +66,9 @@ SIGNATURES = {
     "xf_trainer_step_host": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "xf_trainer_step_device": (_i, [_vp, _vp, _vp, _vp, _u32, _u32]),
     "xf_trainer_predict_host": (_i, [_vp, _vp, _vp, _u32, _u32, _vp]),
+    "xf_trainer_step_host_values": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "xf_trainer_step_device_values": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32]),
+    "xf_trainer_predict_host_values": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "xf_trainer_init_push": (_i, [_vp]),
     "xf_trainer_get_loss": (_i, [_vp, _vp, _u32]),
     "xf_trainer_stats": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -371,6 +374,26 @@ class Trainer:
         _check(lib().xf_trainer_step_host(self.h, _p(row_ptr), _p(keys), _p(labels), labels.size, keys.size,
                                           C.byref(loss) if want_loss else None))
         return loss.value if want_loss else None
+
+    def step_host_values(self, row_ptr, keys, vals, labels):
+        """One step of the canonical FM (XF_MODEL_FM_CANONICAL) on host CSR arrays with feature values."""
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint32)
+        keys = np.ascontiguousarray(keys, np.uint64)
+        vals = None if vals is None else np.ascontiguousarray(vals, np.float32)
+        labels = np.ascontiguousarray(labels, np.uint8)
+        loss = C.c_float()
+        _check(lib().xf_trainer_step_host_values(self.h, _p(row_ptr), _p(keys), _p(vals), _p(labels), labels.size, keys.size,
+                                                 C.byref(loss)))
+        return loss.value
+
+    def predict_host_values(self, row_ptr, keys, vals):
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint32)
+        keys = np.ascontiguousarray(keys, np.uint64)
+        vals = None if vals is None else np.ascontiguousarray(vals, np.float32)
+        rows = row_ptr.size - 1
+        out = np.empty(rows, np.float32)
+        _check(lib().xf_trainer_predict_host_values(self.h, _p(row_ptr), _p(keys), _p(vals), rows, keys.size, _p(out)))
+        return out
 
     def step_host_raw(self, row_ptr_addr, keys_addr, labels_addr, rows, nnz, want_loss=True):
         loss = C.c_float()

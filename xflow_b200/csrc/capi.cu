@@ -82,6 +82,7 @@ XF_DLL int xf_table_config_default(xf_table_config* cfg) {
   cfg->capacity = 0;
   cfg->shard_index = 0;
   cfg->num_shards = 1;
+  cfg->canonical_fm = 0;
   return XF_OK;
 }
 
@@ -97,7 +98,7 @@ int xf_table::alloc_table(uint64_t capacity) {
     xf_set_error("table capacity %llu exceeds 2^31 slots", (unsigned long long)capacity);
     return XF_ERR_FULL;
   }
-  const uint32_t stride = xf_row_stride(cfg.latent_dim, cfg.optimizer);
+  const uint32_t stride = xf_row_stride(cfg.latent_dim, cfg.optimizer, cfg.canonical_fm);
   uint8_t* base = nullptr;
   XF_CUDA_TRY(cudaMalloc(&base, capacity * (uint64_t)stride));
   view.base = base;
@@ -208,13 +209,21 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
     xf_set_error("bad table config");
     return XF_ERR_ARG;
   }
+  if (cfg->canonical_fm) {
+    const int K = cfg->latent_dim;
+    if (!(K == 4 || K == 8 || K == 16 || K == 32 || K == 64 || K == 128) || cfg->num_shards != 1) {
+      xf_set_error("canonical_fm needs latent_dim in {4, 8, 16, 32, 64, 128} and a single shard");
+      return XF_ERR_ARG;
+    }
+  }
   XF_CUDA_TRY(cudaSetDevice(cfg->device));
-  // L2 fetch granularity: one sector.  The table is read and written one random 32-byte row at a time; with the
-  // default (64 B) or a whole 128-byte bucket per miss the DRAM read traffic doubles / quadruples (ncu, headline
-  // LR batch: 340 MB at 32 B, 932 MB at 128 B) for a 3 % shorter kernel — the kernels are bound by the request
-  // rate, not by DRAM.  A hint: the driver may ignore it.  XFLOW_L2_FETCH = 32 / 64 / 128.
+  // L2 fetch granularity = one probing bucket (LR: 4 rows = one 128-byte line), so that the collision probes of
+  // a bucket find the line the first probe fetched.  It costs DRAM read traffic (ncu, headline LR batch: 340 MB at
+  // 32 B, 932 MB at 128 B, DRAM 33 % busy) and buys time: 0.447 ms against 0.522 ms per batch with 32-byte fetches
+  // — the kernels are bound by the request rate, not by DRAM bytes.  A hint: the driver may
+  // ignore it.  XFLOW_L2_FETCH = 32 / 64 / 128 overrides.
   {
-    int fetch = 32;
+    int fetch = 128;
     const char* fe = getenv("XFLOW_L2_FETCH");
     if (fe && (atoi(fe) == 32 || atoi(fe) == 64 || atoi(fe) == 128)) fetch = atoi(fe);
     if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch) != cudaSuccess) cudaGetLastError();
@@ -239,6 +248,7 @@ XF_DLL int xf_table_create(xf_table** out, const xf_table_config* cfg) {
   else v.v_init = (v.opt == XF_OPT_FTRL) ? XF_INIT_COUNTER : XF_INIT_DEFAULT;
   v.size = t->d_size;
   v.error = t->d_error;
+  v.canon = cfg->canonical_fm ? 1 : 0;
   XF_CUDA_TRY(cudaHostAlloc(&t->h_size_ring, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
   for (int i = 0; i < 4; ++i) XF_CUDA_TRY(cudaEventCreateWithFlags(&t->size_ev[i], cudaEventDisableTiming));
   // K == 0 (LR) tables fold the optimizer step into the next touch of a row (step.cu); K > 0 tables
@@ -620,6 +630,11 @@ XF_DLL int xf_shard_of(uint64_t key, int num_shards) {
 XF_DLL int xf_trainer_create(xf_trainer** out, xf_table* table, xf_comm* comm, const xf_trainer_config* cfg) {
   if (!out || !table || !cfg) { xf_set_error("null argument"); return XF_ERR_ARG; }
   if (cfg->model == XF_MODEL_FM && table->view.K <= 0) { xf_set_error("FM needs latent_dim > 0"); return XF_ERR_ARG; }
+  if (cfg->model == XF_MODEL_FM_CANONICAL && (!table->view.canon || comm)) {
+    xf_set_error("XF_MODEL_FM_CANONICAL needs a table created with canonical_fm = 1 and no comm");
+    return XF_ERR_ARG;
+  }
+  if (cfg->model != XF_MODEL_FM_CANONICAL && table->view.canon) { xf_set_error("canonical tables serve XF_MODEL_FM_CANONICAL only"); return XF_ERR_ARG; }
   if (cfg->model == XF_MODEL_LR && table->view.K != 0) { xf_set_error("LR needs latent_dim == 0"); return XF_ERR_ARG; }
   if (cfg->max_rows == 0 || cfg->max_nnz == 0) { xf_set_error("max_rows/max_nnz must be > 0"); return XF_ERR_ARG; }
   XF_CUDA_TRY(cudaSetDevice(table->cfg.device));
@@ -670,7 +685,7 @@ XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
   if (tr->mg) xf_mg_destroy(tr);
   for (int i = 0; i < 2; ++i) {
     XfBatchBuf& b = tr->buf[i];
-    b.row_ptr.release(); b.keys.release(); b.labels.release(); b.ids.release();
+    b.row_ptr.release(); b.keys.release(); b.labels.release(); b.ids.release(); b.vals.release();
     b.h_row_ptr.release(); b.h_keys.release(); b.h_labels.release();
     cudaEventDestroy(b.copied); cudaEventDestroy(b.consumed); cudaEventDestroy(b.staged);
   }
@@ -705,7 +720,8 @@ static int xf_check_batch(xf_trainer* tr, uint32_t rows, uint32_t nnz) {
 
 // the step proper, on device-resident CSR; mode 0 = train, 1 = predict
 static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys,
-                               const uint8_t* d_labels, uint32_t rows, uint32_t nnz, int mode, float* d_abs) {
+                               const uint8_t* d_labels, uint32_t rows, uint32_t nnz, int mode, float* d_abs,
+                               const float* d_vals = nullptr) {
   xf_table* t = tr->table;
   if (rows == 0 && !tr->mg) return XF_OK;     // sharded: an empty batch still takes part in the exchange
   if (!tr->mg) XF_TRY(t->ensure_room(nnz));  // the sharded path sizes the shard from what it receives
@@ -739,11 +755,17 @@ static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const 
     XF_CUDA_TRY(cudaGetLastError());
     return XF_OK;
   }
-  const uint32_t extra = xf_step_touched_extra(t->view.K, (int)rows);
+  const bool canon = tr->cfg.model == XF_MODEL_FM_CANONICAL;
+  const uint32_t extra = canon ? 0u : xf_step_touched_extra(t->view.K, (int)rows);
   XF_TRY(tr->touched.ensure(((size_t)nnz + extra) * 4));
-  xf_launch_step(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(), nnz,
-                 (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
-                 mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
+  if (canon)
+    xf_launch_step_fmc(t->view, d_row_ptr, d_keys, d_vals, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
+                       (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
+                       mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
+  else
+    xf_launch_step(t->view, d_row_ptr, d_keys, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(), nnz,
+                   (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
+                   mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
   ++tr->launches;
   if (prof) {
     XF_CUDA_TRY(cudaEventRecord(pe[1], st));
@@ -855,6 +877,81 @@ XF_DLL int xf_trainer_predict_host(xf_trainer* tr, const uint32_t* row_ptr, cons
   XF_TRY(b.labels.ensure((size_t)rows + 1));  // unused by mode 1 but must be a valid pointer
   XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows,
                              nnz, 1, nullptr));
+  XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
+  XF_CUDA_TRY(cudaMemcpyAsync(pctr_out, tr->pctr.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  return tr->table->check_error();
+}
+
+// ---- the same entry points with feature values (XF_MODEL_FM_CANONICAL, step_fmc.cu)
+XF_DLL int xf_trainer_step_device_values(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys,
+                                         const float* d_vals, const uint8_t* d_labels, uint32_t rows, uint32_t nnz) {
+  if (!tr || !d_row_ptr || !d_keys || !d_labels) return XF_ERR_ARG;
+  if (tr->cfg.model != XF_MODEL_FM_CANONICAL) { xf_set_error("feature values need XF_MODEL_FM_CANONICAL"); return XF_ERR_ARG; }
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  XF_TRY(xf_step_device_impl(tr, d_row_ptr, d_keys, d_labels, rows, nnz, 0, nullptr, d_vals));
+  ++tr->n_steps;
+  tr->n_rows += rows;
+  tr->n_nnz += nnz;
+  tr->last_rows = rows;
+  return XF_OK;
+}
+
+static int xf_upload_vals(xf_trainer* tr, XfBatchBuf& b, const float* vals, uint32_t nnz, const float** d_vals) {
+  *d_vals = nullptr;
+  if (!vals || !nnz) return XF_OK;
+  XF_TRY(b.vals.ensure((size_t)nnz * 4));
+  // pageable or pinned: a plain stream-ordered copy on the table stream (the values are a small part of a batch)
+  XF_CUDA_TRY(cudaMemcpyAsync(b.vals.p, vals, (size_t)nnz * 4, cudaMemcpyHostToDevice, tr->table->stream));
+  *d_vals = b.vals.as<float>();
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_step_host_values(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys, const float* vals,
+                                       const uint8_t* labels, uint32_t rows, uint32_t nnz, float* mean_abs_loss) {
+  if (!tr || !row_ptr || (!keys && nnz) || !labels) return XF_ERR_ARG;
+  if (tr->cfg.model != XF_MODEL_FM_CANONICAL) { xf_set_error("feature values need XF_MODEL_FM_CANONICAL"); return XF_ERR_ARG; }
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  if (rows == 0) { if (mean_abs_loss) *mean_abs_loss = 0.f; return XF_OK; }
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const int slot = (int)(tr->step_index & 1);
+  XfBatchBuf& b = tr->buf[slot];
+  ++tr->step_index;
+  XF_TRY(xf_upload_batch(tr, b, row_ptr, keys, labels, rows, nnz));
+  cudaStream_t st = tr->table->stream;
+  const float* d_vals = nullptr;
+  XF_TRY(xf_upload_vals(tr, b, vals, nnz, &d_vals));
+  XF_CUDA_TRY(cudaMemsetAsync(tr->d_abs_loss + slot, 0, sizeof(float), st));
+  XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows, nnz, 0,
+                             tr->d_abs_loss + slot, d_vals));
+  XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
+  ++tr->n_steps;
+  tr->n_rows += rows;
+  tr->n_nnz += nnz;
+  tr->last_rows = rows;
+  XF_CUDA_TRY(cudaMemcpyAsync(tr->h_abs_loss + slot, tr->d_abs_loss + slot, sizeof(float), cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));  // also: `vals` may be reused by the caller
+  if (mean_abs_loss) *mean_abs_loss = tr->h_abs_loss[slot] / (float)rows;
+  return tr->table->check_error();
+}
+
+XF_DLL int xf_trainer_predict_host_values(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys, const float* vals,
+                                          uint32_t rows, uint32_t nnz, float* pctr_out) {
+  if (!tr || !row_ptr || (!keys && nnz) || !pctr_out) return XF_ERR_ARG;
+  if (tr->cfg.model != XF_MODEL_FM_CANONICAL) { xf_set_error("feature values need XF_MODEL_FM_CANONICAL"); return XF_ERR_ARG; }
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  if (rows == 0) return XF_OK;
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const int slot = (int)(tr->step_index & 1);
+  XfBatchBuf& b = tr->buf[slot];
+  ++tr->step_index;
+  XF_TRY(xf_upload_batch(tr, b, row_ptr, keys, nullptr, rows, nnz));
+  cudaStream_t st = tr->table->stream;
+  XF_TRY(b.labels.ensure((size_t)rows + 1));
+  const float* d_vals = nullptr;
+  XF_TRY(xf_upload_vals(tr, b, vals, nnz, &d_vals));
+  XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows, nnz, 1,
+                             nullptr, d_vals));
   XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
   XF_CUDA_TRY(cudaMemcpyAsync(pctr_out, tr->pctr.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
   XF_CUDA_TRY(cudaStreamSynchronize(st));

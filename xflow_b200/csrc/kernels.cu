@@ -142,6 +142,11 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
         const uint64_t tok = (i_phys < (uint64_t)extra_base) ? i_phys : (uint64_t)__ldg(slots + i_phys + extra_n);
         xf_ldv<VEC>(v0_side + tok * (uint64_t)K + q * VEC, p0);
       }
+      // canonical FM tables (step_fmc.cu): gv[k] = A[k] - v[k] * L2, A a float per coordinate behind the state
+      float ca0[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) ca0[e] = 0.f;
+      if (SLOTG && t.canon && has0) xf_ldv<VEC>(xf_row_ca(t, rowp) + q * VEC, ca0);
       // fused step: gv[k] = Aq - v[k] * L (table.cuh); every lane of the group reads the same 16 bytes
       double accL = 0.0, accA = 0.0;
       if (SLOTG && has0) {
@@ -196,8 +201,19 @@ xf_k_update(XfTableView t, const uint32_t* __restrict__ slots, uint64_t n, int t
                 xf_ldv<VEC>(v0_side + tok * (uint64_t)K + k, vp0);
               }
             }
+            if (t.canon) {
+              float ca[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) g[e] = xf_div_rows((float)(accA - (double)vp0[e] * accL), rows);
+              for (int e = 0; e < VEC; ++e) ca[e] = ca0[e];
+              if (c != q) xf_ldv<VEC>(xf_row_ca(t, rowp) + k, ca);
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) g[e] = xf_div_rows((float)((double)ca[e] - (double)vp0[e] * accL), rows);
+              const float zero[VEC] = {};
+              xf_stv<VEC>(xf_row_ca(t, rowp) + k, zero);
+            } else {
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) g[e] = xf_div_rows((float)(accA - (double)vp0[e] * accL), rows);
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) g[e] = gv[i * (uint64_t)K + k + e];
@@ -588,7 +604,7 @@ static void xf_launch_update_t(const XfTableView& t, const uint32_t* slots, uint
   // requests but only 2 rows in flight per warp and 90+ registers -> 3x SLOWER than the per-coordinate kernel;
   // off unless XFLOW_UPDATE_WIDE=1 (A/B measurements)
   static const bool wide_on = [] { const char* e = getenv("XFLOW_UPDATE_WIDE"); return e && *e == '1'; }();
-  if (wide_on && t.K > 0 && (t.K & 3) == 0 && t.stride <= 512 && (part & 2)) {
+  if (wide_on && !t.canon && t.K > 0 && (t.K & 3) == 0 && t.stride <= 512 && (part & 2)) {
     int G = 1;
     while (G < (int)(t.stride >> 4)) G <<= 1;
     const int grid = xf_grid_for(n * (uint64_t)G, 256, 8);

@@ -67,3 +67,8 @@ uint32_t xf_acc_touched_extra(int K, uint64_t work_bound);
 void xf_launch_acc_tokens(const XfTableView& t, const uint32_t* slots, const uint32_t* in_rows, const void* rowv,
                           const uint32_t* meta_s, uint32_t cap, uint64_t work_bound, uint32_t* touched,
                           cudaStream_t st);
+
+// canonical per-k FM with feature values (step_fmc.cu)
+void xf_launch_step_fmc(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys, const float* vals,
+                        const uint8_t* labels, int B, int mode, uint32_t* touched, float* loss_out, float* pctr_out,
+                        float* abs_loss_sum, cudaStream_t st);

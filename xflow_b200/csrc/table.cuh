@@ -81,6 +81,9 @@ struct XfTableView {
   // count (the divisor of lr_worker.cc:116-118).  Every reader applies a pending step on the fly.
   int lazy;
   const uint32_t* rows_by_seq;
+  // canonical per-k FM (step_fmc.cu; not the reference's model): rows carry K more float
+  // accumulators A[k] = sum_occ loss x S_k behind the optimizer state
+  int canon;
 };
 #define XF_TAG_LOCKED 0xFFFFFFFFu  // never a batch number (the sequence ring is far smaller)
 #define XF_FIX_SCALE 134217728.0          // 2^27: residual sums of lazy tables are 48-bit integers of this unit
@@ -88,9 +91,12 @@ struct XfTableView {
 #define XF_TAG_MASK 0xFFFFull               // lazy rows: low 16 bits of the word at byte 24
 
 __host__ __device__ inline uint32_t xf_acc_off(int K) { return (32u + 4u * (uint32_t)K + 15u) & ~15u; }
-__host__ __device__ inline uint32_t xf_row_stride(int K, int opt) {
+__host__ __device__ inline uint32_t xf_ca_off(int K, int opt) {  // canonical FM: the A[K] accumulators
+  return xf_acc_off(K) + 16u + ((opt == XF_OPT_FTRL) ? 8u * (uint32_t)K : 0u);
+}
+__host__ __device__ inline uint32_t xf_row_stride(int K, int opt, int canon = 0) {
   if (K <= 0) return 32u;
-  uint32_t bytes = xf_acc_off(K) + 16u + ((opt == XF_OPT_FTRL) ? 8u * (uint32_t)K : 0u);
+  uint32_t bytes = xf_ca_off(K, opt) + (canon ? 4u * (uint32_t)K : 0u);
   return (bytes + 31u) & ~31u;
 }
 
@@ -154,6 +160,7 @@ __device__ __forceinline__ float* xf_row_v(uint8_t* row) { return reinterpret_ca
 __device__ __forceinline__ double* xf_row_acc(uint8_t* row, int K) { return reinterpret_cast<double*>(row + xf_acc_off(K)); }
 __device__ __forceinline__ float* xf_row_nv(uint8_t* row, int K) { return reinterpret_cast<float*>(row + xf_acc_off(K) + 16); }
 __device__ __forceinline__ float* xf_row_zv(uint8_t* row, int K) { return xf_row_nv(row, K) + K; }
+__device__ __forceinline__ float* xf_row_ca(const XfTableView& t, uint8_t* row) { return reinterpret_cast<float*>(row + xf_ca_off(t.K, t.opt)); }
 
 struct XfHead {
   uint64_t key;

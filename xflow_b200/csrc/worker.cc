@@ -362,10 +362,13 @@ void WorkerBase::predict(int rank_arg, int block) {
   if (!host_parse) ensure_trainer_for_block(block_bytes);
   std::vector<float> pctr_buf;
   std::vector<uint8_t> label_buf;
-  // the metric is computed on the device (sort + reductions, metric.cu); the predictions come back only because
-  // the reference writes every one of them to pred_<rank>_<block>.txt
+  // XFLOW_DEVICE_METRIC=1: the metric is computed on the device (radix sort + integer rank sums, metric.cu) and the
+  // printed numbers come from there.  Default: the host restatement of Base::calculate_auc, whose float
+  // accumulators and std::sort tie order are what the reference's own printout (and the golden fixtures) contain;
+  // the predictions come back to the host either way, the reference writes every one to pred_<rank>_<block>.txt.
   xf_metric* metric = nullptr;
-  if (!host_parse) must(xf_metric_create(&metric, Server::Get()->device()), "xf_metric_create");
+  if (!host_parse && env_int("XFLOW_DEVICE_METRIC", 0) != 0)
+    must(xf_metric_create(&metric, Server::Get()->device()), "xf_metric_create");
   if (!host_parse) {
     if (feeding) open_loader(test_data_path, block_bytes);
     else open_loader("/dev/null", block_bytes);  // nothing to feed: every block is empty
@@ -374,9 +377,13 @@ void WorkerBase::predict(int rank_arg, int block) {
       pctr_buf.resize(thread_size + 1);
       label_buf.resize(thread_size + 1);
       for (uint32_t i = 0; i < (uint32_t)core_num; ++i) {
-        must(xf_trainer_predict_ingested_metric(trainer_, i * thread_size, (i + 1) * thread_size, metric,
-                                                feeding ? pctr_buf.data() : nullptr, feeding ? label_buf.data() : nullptr),
-             "xf_trainer_predict_ingested_metric");
+        if (metric)
+          must(xf_trainer_predict_ingested_metric(trainer_, i * thread_size, (i + 1) * thread_size, metric,
+                                                  feeding ? pctr_buf.data() : nullptr, feeding ? label_buf.data() : nullptr),
+               "xf_trainer_predict_ingested_metric");
+        else
+          must(xf_trainer_predict_ingested(trainer_, i * thread_size, (i + 1) * thread_size, pctr_buf.data(), label_buf.data()),
+               "xf_trainer_predict_ingested");
         if (!feeding) continue;
         for (uint32_t r = 0; r < thread_size; ++r) {
           auc_key ak;
@@ -407,7 +414,7 @@ void WorkerBase::predict(int rank_arg, int block) {
     xf_metric_destroy(metric);
   }
   if (!feeding) return;
-  if (metric && env_int("XFLOW_HOST_METRIC", 0) == 0) {
+  if (metric) {
     // Base::calculate_auc's printout (base.h:101-109) from the device-side metric
     last_logloss = dm[0];
     last_auc = dm[1];
