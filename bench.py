@@ -467,6 +467,8 @@ def main():
     torch.cuda.set_device(local)
     comm = None
     dist = None
+    if world == 1 and os.environ.get("XFLOW_MG_FORCE") == "1":
+        comm = api.Comm(api.Comm.new_id(), 0, 1, local)   # profiling: the sharded step on one GPU (all keys local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

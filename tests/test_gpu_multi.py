@@ -39,6 +39,13 @@ def _batch(case, world, rank, rnd):
     return rp, keys, lab
 
 
+def _imported(case, world):
+    ks = np.unique(np.concatenate([_batch(case, world, r, 0)[1][:300] for r in range(world)]))
+    rng = np.random.default_rng(77)
+    return (ks, rng.normal(0, 0.3, ks.size).astype(np.float32), rng.uniform(0, 2, ks.size).astype(np.float32),
+            rng.normal(0, 1, ks.size).astype(np.float32))
+
+
 def _all_keys(case, world):
     return np.unique(np.concatenate([_batch(case, world, r, rnd)[1] for r in range(world) for rnd in range(ROUNDS)] +
                                     [np.zeros(1, np.uint64)]))
@@ -63,6 +70,12 @@ def _worker(rank, world, id_path, case, ret):
     max_nnz = max(_batch(case, world, r, rnd)[1].size for r in range(world) for rnd in range(ROUNDS)) + 8
     tr = A.Trainer(table, model=model, max_rows=case["B"], max_nnz=max_nnz, keep_loss=True, comm=comm)
     tr.init_push()
+    if case.get("imported"):
+        # rows whose weight is NOT f(z, n) (a model file loaded before training): the lazy table keeps such a
+        # weight beside the state and the Push takes a fresh look at those rows instead of the stashed one
+        ik, iw, inw, izw = _imported(case, world)
+        mine = np.array([A.shard_of(int(k), world) == rank for k in ik])
+        table.import_(ik[mine], w=iw[mine], nw=inw[mine], zw=izw[mine])
     comm.barrier()
     losses = []
     for rnd in range(ROUNDS):
@@ -91,12 +104,13 @@ def _worker(rank, world, id_path, case, ret):
 CASES = {
     "lr_ftrl": dict(model="lr", opt="ftrl", K=0, B=4096, D=32, space=200000, dist="uniform"),
     "lr_ftrl_zipf_edges": dict(model="lr", opt="ftrl", K=0, B=4096, D=24, space=10 ** 9, dist="zipf", edges=True, ragged=True),
+    "lr_ftrl_imported": dict(model="lr", opt="ftrl", K=0, B=2048, D=32, space=100000, dist="uniform", imported=True),
     "lr_sgd": dict(model="lr", opt="sgd", K=0, B=2048, D=16, space=50000, dist="uniform"),
     "fm_ftrl_k8": dict(model="fm", opt="ftrl", K=8, B=4096, D=32, space=200000, dist="uniform"),
     "fm_sgd_k4": dict(model="fm", opt="sgd", K=4, B=4096, D=32, space=200000, dist="uniform"),
     "fm_ftrl_k16_zipf": dict(model="fm", opt="ftrl", K=16, B=4096, D=32, space=10 ** 8, dist="zipf", edges=True),
 }
-RUNS = [(2, "lr_ftrl"), (2, "lr_ftrl_zipf_edges"), (2, "lr_sgd"), (2, "fm_ftrl_k8"), (2, "fm_sgd_k4"), (2, "fm_ftrl_k16_zipf"),
+RUNS = [(2, "lr_ftrl"), (2, "lr_ftrl_imported"), (2, "lr_ftrl_zipf_edges"), (2, "lr_sgd"), (2, "fm_ftrl_k8"), (2, "fm_sgd_k4"), (2, "fm_ftrl_k16_zipf"),
         (4, "lr_ftrl_zipf_edges"), (4, "fm_ftrl_k16_zipf"), (8, "lr_ftrl_zipf_edges"), (8, "fm_ftrl_k16_zipf")]
 
 
@@ -106,6 +120,9 @@ def _lockstep_oracle(case, world, exact):
     t = O.Table(K=K, opt=oopt, init_mode=O.INIT_COUNTER, seed=9)
     for _ in range(world):
         t.init_push()
+    if case.get("imported"):
+        ik, iw, inw, izw = _imported(case, world)
+        t.import_(ik, w=iw, nw=inw, zw=izw)
     losses = {r: [] for r in range(world)}
     uniq = {r: 0 for r in range(world)}
 

@@ -662,7 +662,10 @@ XF_DLL int xf_trainer_create(xf_trainer** out, xf_table* table, xf_comm* comm, c
   XF_CUDA_TRY(cudaMemsetAsync(tr->d_unique_total, 0, sizeof(unsigned long long), table->stream));
   XF_CUDA_TRY(cudaMemsetAsync(tr->d_abs_loss, 0, 2 * sizeof(float), table->stream));
   XF_CUDA_TRY(cudaStreamSynchronize(table->stream));
-  if (comm && xf_comm_nranks(comm) > 1) {
+  // XFLOW_MG_FORCE=1: run the sharded step even with a one-rank communicator (profiling the owner / worker
+  // kernels of comm.cu under ncu, which cannot wrap a multi-rank command)
+  const char* force_mg = getenv("XFLOW_MG_FORCE");
+  if (comm && (xf_comm_nranks(comm) > 1 || (force_mg && *force_mg == '1'))) {
     if (table->cfg.num_shards != xf_comm_nranks(comm) || table->cfg.shard_index != xf_comm_rank(comm)) {
       xf_set_error("table shard (%d of %d) does not match comm rank (%d of %d)", table->cfg.shard_index,
                    table->cfg.num_shards, xf_comm_rank(comm), xf_comm_nranks(comm));

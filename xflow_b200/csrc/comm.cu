@@ -213,9 +213,11 @@ struct XfMg {
   XfPeers peers;            // every rank's slab as mapped here (peers.slab[rank] == slab)
   XfDevBuf slots, tok_pos[2], bucket_cnt[2], rowv_local, touched;
   XfDevBuf side_v;  // FM, S > 1: latent rows as pulled by the tokens of sources >= 1 (see xf_k_pull_tokens)
-  XfDevBuf stash;   // LR, lazy table: the 32-byte row of every routed token as the Pull found it, for the Push
+  XfDevBuf stash;   // LR, lazy table: the state words (16 B) of every routed token's row as the Pull found them, for the Push
   uint32_t touched_extra = 0;
   cudaStream_t st2 = nullptr;
+  cudaStream_t st3 = nullptr;   // token-count readbacks (a copy engine switch costs the table stream ~40 us)
+  cudaEvent_t ev_meta = nullptr;
   cudaEvent_t ev_rows_done[2] = {nullptr, nullptr};  // tok_pos[p] no longer read by the table stream
   uint64_t step_no = 0;
   unsigned long long timeout_ns = 120ull * 1000000000ull;
@@ -321,12 +323,14 @@ int xf_mg_create(xf_trainer* tr) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&mg->st2, cudaStreamNonBlocking, lo) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
+    if (cudaStreamCreateWithFlags(&mg->st3, cudaStreamNonBlocking) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
+    if (cudaEventCreateWithFlags(&mg->ev_meta, cudaEventDisableTiming) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
     if ((rc = mg->slots.ensure((size_t)S * mg->cap * 4)) != XF_OK) break;
     if ((rc = mg->rowv_local.ensure((size_t)mg->max_rows * 8 + 16)) != XF_OK) break;
     const bool lazy = tr->table->view.lazy != 0;
     {
       const char* se = getenv("XFLOW_MG_STASH");  // A/B: 0 = the Push handler loads the rows itself
-      if (lazy && !(se && *se == '0') && (rc = mg->stash.ensure((size_t)S * mg->cap * 32)) != XF_OK) break;
+      if (lazy && !(se && *se == '0') && (rc = mg->stash.ensure((size_t)S * mg->cap * 16)) != XF_OK) break;
     }
     if (!lazy) {
       mg->touched_extra = xf_acc_touched_extra(mg->K, (uint64_t)mg->cap);
@@ -365,6 +369,7 @@ void xf_mg_destroy(xf_trainer* tr) {
   if (!mg) return;
   cudaStream_t st = tr->table->stream;
   if (mg->st2) cudaStreamSynchronize(mg->st2);
+  if (mg->st3) cudaStreamSynchronize(mg->st3);
   cudaStreamSynchronize(st);
   if (mg->trace && mg->tsteps) {
     // skip the first steps (population / allocation); events were recorded without any extra sync
@@ -406,6 +411,8 @@ void xf_mg_destroy(xf_trainer* tr) {
   for (int i = 0; i < 4; ++i) if (mg->meta_ev[i]) cudaEventDestroy(mg->meta_ev[i]);
   if (mg->h_meta) cudaFreeHost(mg->h_meta);
   if (mg->st2) cudaStreamDestroy(mg->st2);
+  if (mg->st3) cudaStreamDestroy(mg->st3);
+  if (mg->ev_meta) cudaEventDestroy(mg->ev_meta);
   for (auto& e : mg->tev) cudaEventDestroy(e);
   delete mg;
   tr->mg = nullptr;
@@ -478,11 +485,16 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
                         mode == 0 ? mg->stash.p : nullptr, st);
   if (pm) XF_CUDA_TRY(cudaEventRecord(pm[1], st));
   {
+    // how many tokens arrived, for the next steps' growth checks: read back on a side stream (the counts are
+    // final once the KEYS wait has passed; DONE is signalled from the same side stream, behind the copy, because
+    // the sources may overwrite the counts after that)
     const int slot = (int)(step & 3);
     if (!mg->meta_inflight[slot]) {
+      XF_CUDA_TRY(cudaEventRecord(mg->ev_meta, st));
+      XF_CUDA_TRY(cudaStreamWaitEvent(mg->st3, mg->ev_meta, 0));
       XF_CUDA_TRY(cudaMemcpyAsync(mg->h_meta + (size_t)slot * XF_MG_MAX_SHARDS * 4, meta_p, XF_MG_MAX_SHARDS * 4 * sizeof(uint32_t),
-                                  cudaMemcpyDeviceToHost, st));
-      XF_CUDA_TRY(cudaEventRecord(mg->meta_ev[slot], st));
+                                  cudaMemcpyDeviceToHost, mg->st3));
+      XF_CUDA_TRY(cudaEventRecord(mg->meta_ev[slot], mg->st3));
       mg->meta_inflight[slot] = true;
     }
   }
@@ -508,7 +520,9 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
     // forward only: nothing to push; the routed tokens are no longer needed
     XF_MG_MARK(5);
     XF_MG_MARK(6);
-    xf_launch_signal(mg->peers, L, S, me, XF_F_DONE, step, p, nullptr, 0, st);
+    XF_CUDA_TRY(cudaEventRecord(mg->ev_meta, st));
+    XF_CUDA_TRY(cudaStreamWaitEvent(mg->st3, mg->ev_meta, 0));
+    xf_launch_signal(mg->peers, L, S, me, XF_F_DONE, step, p, nullptr, 0, mg->st3);
     ++tr->launches;
     if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) { cudaEventRecord(mg->tev[mg->tsteps * XF_TR_NMARK + 7], st); ++mg->tsteps; }
     XF_CUDA_TRY(cudaGetLastError());
@@ -532,7 +546,7 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
       XF_TRY(t->next_seq());
       xf_launch_push_tokens_lr(t->view, slots_s, rows_s, reinterpret_cast<const float*>(rowv_s), meta_s, cap, work, t->seq,
                                t->d_rows_by_seq, uniq_s,
-                               mg->stash.p ? (const uint8_t*)mg->stash.p + (size_t)s * cap * 32 : nullptr, st);
+                               mg->stash.p ? (const uint8_t*)mg->stash.p + (size_t)s * cap * 16 : nullptr, st);
       ++tr->launches;
     } else {
       xf_launch_acc_tokens(t->view, slots_s, rows_s, rowv_s, meta_s, cap, work, mg->touched.as<uint32_t>(), st);
@@ -545,7 +559,11 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
   }
   if (pm) XF_CUDA_TRY(cudaEventRecord(pm[3], st));
   XF_MG_MARK(6);
-  xf_launch_signal(mg->peers, L, S, me, XF_F_DONE, step, p, nullptr, 0, st);
+  // DONE is consumed two steps later (the sources' routing): signalled from the side stream, behind the count
+  // readback (which must precede it, see above), so that its system-scope release does not sit on the table stream
+  XF_CUDA_TRY(cudaEventRecord(mg->ev_meta, st));
+  XF_CUDA_TRY(cudaStreamWaitEvent(mg->st3, mg->ev_meta, 0));
+  xf_launch_signal(mg->peers, L, S, me, XF_F_DONE, step, p, nullptr, 0, mg->st3);
   ++tr->launches;
   if (mg->trace && mg->tsteps < XF_MG_TRACE_STEPS) { cudaEventRecord(mg->tev[mg->tsteps * XF_TR_NMARK + 7], st); ++mg->tsteps; }
   XF_CUDA_TRY(cudaGetLastError());

@@ -44,7 +44,8 @@ __global__ void xf_k_signal(XfPeers peers, XfSlabLayout L, int S, int me, int fl
     m[0] = bucket_cnt[q];
     m[1] = rows;
   }
-  __threadfence_system();
+  // the release orders everything before it in this stream (the producing kernel included) ahead of the flag;
+  // a separate fence in front of it would drain the peer stores a second time
   xf_st_release_sys(reinterpret_cast<uint64_t*>(slab + L.off_flags) + (size_t)flag * XF_MG_MAX_SHARDS + me, step);
 }
 
@@ -190,14 +191,14 @@ xf_k_pull_tokens(XfTableView t, const uint64_t* __restrict__ in_keys, const uint
     const int64_t r = xf_probe_from<true>(t, key, home, h);
     float w = 0.f, st = 0.f, qt = 0.f;
     if (!FM && stash != nullptr) {
-      // LR, lazy table: the row exactly as found goes to the Push handler of this step (streaming, 32 B per
-      // token): its open then needs no load of the row — one row-touching instruction less per token
-      XfHead raw = h;
-      if (r < 0) raw.key = XF_EMPTY_KEY;
-      uint4* sp = stash + 2 * ((uint64_t)s * cap + i);
-      __stcs(sp, make_uint4((uint32_t)raw.key, (uint32_t)(raw.key >> 32), (uint32_t)__double_as_longlong(raw.g),
-                            (uint32_t)((unsigned long long)__double_as_longlong(raw.g) >> 32)));
-      __stcs(sp + 1, make_uint4(__float_as_uint(raw.w), __float_as_uint(raw.n), __float_as_uint(raw.z), raw.flags));
+      // LR, lazy table: the row's state words exactly as found go to the Push handler of this step (streaming,
+      // 16 B per token): its open then needs no load of the row — one row-touching instruction less per token.
+      // A row that carries an imported weight beside its state (bytes 8..15, rare) is marked with the tag no
+      // batch ever has, and the Push takes a fresh look at it instead.
+      const uint64_t q1 = xf_raw_q1(h), q2 = xf_raw_q2(h);
+      uint64_t q3 = xf_raw_q3(h);
+      if ((uint32_t)(q1 >> 32) == xf_lazy_check(q2)) q3 |= XF_TAG_MASK;
+      __stcs(stash + ((uint64_t)s * cap + i), make_uint4((uint32_t)q2, (uint32_t)(q2 >> 32), (uint32_t)q3, (uint32_t)(q3 >> 32)));
     }
     if (r >= 0) {
       xf_apply_pending(t, h);  // lazy LR tables: the value the reference's server would hold
@@ -321,7 +322,7 @@ __global__ void xf_k_bcast_rowv(const uint32_t* __restrict__ src, uint32_t n_wor
 // of THIS push is applied by the next touch (next opener, or on the fly by any reader) with divisor
 // rows_by_seq[seq] = the source's batch size: exactly one FTRL/SGD step per (source, key), sources in rank order
 // because the S launches are stream-ordered.  One token per lane; with the look at the row that this step's Pull
-// stashed (32 B per token, streaming) a token costs ONE row-touching instruction; lanes of a warp that hit the
+// stashed (16 B per token, streaming) a token costs ONE row-touching instruction; lanes of a warp that hit the
 // same row elect one of them.
 __global__ void __launch_bounds__(256)
 xf_k_push_tokens_lr(XfTableView t, const uint32_t* __restrict__ slots, const uint32_t* __restrict__ in_rows,
@@ -337,58 +338,98 @@ xf_k_push_tokens_lr(XfTableView t, const uint32_t* __restrict__ slots, const uin
   const uint32_t wpb = blockDim.x >> 5;
   const uint32_t gwarp = blockIdx.x * wpb + (threadIdx.x >> 5);
   const uint32_t nwarps = gridDim.x * wpb;
-  for (uint32_t base = gwarp * 32; base < n; base += nwarps * 32) {
-    const uint32_t i = base + lane;
-    uint32_t s = XF_NO_SLOT;
-    float l = 0.f;
-    if (i < n) {
-      s = __ldcs(slots + i);
-      l = __ldcg(rowv + __ldcs(in_rows + i));
-    }
-    const bool valid = s != XF_NO_SLOT;
-    uint8_t* rowp = xf_row(t, valid ? s : 0);
-    uint64_t q1 = 0ull, q2 = 0ull, q3 = (uint64_t)seq;  // invalid lanes: "open", nothing to do
-    if (valid) {
-      if (stash != nullptr) {
-        // the row as this step's Pull found it (coalesced, streaming) instead of a load of the row
-        const uint4 a = __ldcs(stash + 2 * (uint64_t)i), b = __ldcs(stash + 2 * (uint64_t)i + 1);
-        q1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
-        q2 = (uint64_t)b.x | ((uint64_t)b.y << 32);
-        q3 = (uint64_t)b.z | ((uint64_t)b.w << 32);
+  // Two groups of 32 tokens per warp and iteration: both deposits are issued before any result is looked at, and
+  // the coalesced inputs of the NEXT iteration (slot, row index, stashed state words) are requested before this
+  // iteration's atomics go out.  ncu on the first version (one group, nothing ahead): 27 G requests/s with 53
+  // long-scoreboard stall cycles per issue — a chain of four dependent round trips per 32 tokens.
+  const bool have_stash = stash != nullptr;
+  uint32_t s_n[2], r_n[2];
+  uint4 b_n[2];
+#define XF_PUSH_FETCH(base_)                                                        \
+  _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                    \
+    const uint32_t i = (base_) + 32u * u + lane;                                     \
+    s_n[u] = XF_NO_SLOT; r_n[u] = 0u; b_n[u] = make_uint4(0u, 0u, 0u, 0u);            \
+    if (i < n) {                                                                     \
+      s_n[u] = __ldcs(slots + i);                                                    \
+      r_n[u] = __ldcs(in_rows + i);                                                  \
+      if (have_stash) b_n[u] = __ldcs(stash + (uint64_t)i);                          \
+    }                                                                                \
+  }
+  uint32_t base = gwarp * 64;
+  if (base < n) { XF_PUSH_FETCH(base) }
+  for (; base < n; base += nwarps * 64) {
+    uint32_t s[2];
+    float l[2];
+    uint64_t q1[2], q2[2], q3[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      s[u] = s_n[u];
+      l[u] = 0.f;
+      q1[u] = 0ull; q2[u] = 0ull; q3[u] = (uint64_t)seq;  // invalid lanes: "open", nothing to do
+      if (s[u] == XF_NO_SLOT) continue;
+      l[u] = __ldcg(rowv + r_n[u]);
+      if (have_stash) {
+        // the row's state as this step's Pull found it (coalesced, streaming) instead of a load of the row
+        q2[u] = (uint64_t)b_n[u].x | ((uint64_t)b_n[u].y << 32);
+        q3[u] = (uint64_t)b_n[u].z | ((uint64_t)b_n[u].w << 32);
       } else {
-        const XfHead h = xf_load_head(rowp);
-        q1 = xf_raw_q1(h);
-        q2 = xf_raw_q2(h);
-        q3 = xf_raw_q3(h);
+        const XfHead h = xf_load_head(xf_row(t, s[u]));
+        q1[u] = xf_raw_q1(h);
+        q2[u] = xf_raw_q2(h);
+        q3[u] = xf_raw_q3(h);
       }
     }
-    // tokens of this warp that hit the same row: the lowest lane deposits the group's residuals
-    const unsigned grp = __match_any_sync(0xffffffffu, valid ? s : (0xFFFFFF00u | (uint32_t)lane));
-    const bool lead = valid && lane == __ffs(grp) - 1;
-    long long fix = valid ? xf_fix_of(l) : 0ll;
-    if (__any_sync(0xffffffffu, valid && __popc(grp) > 1)) {
-      long long sum = 0ll;
-      for (int b = 0; b < 32; ++b) {
-        const long long o = __shfl_sync(0xffffffffu, fix, b);
-        if ((grp >> b) & 1u) sum += o;
+    if (base + nwarps * 64 < n) { XF_PUSH_FETCH(base + nwarps * 64) }
+    bool lead[2], issued[2], reload[2];
+    long long fix[2];
+    uint64_t q2n[2], o2[2], o3[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool valid = s[u] != XF_NO_SLOT;
+      // tokens of this group that hit the same row: the lowest lane deposits the group's residuals
+      const unsigned grp = __match_any_sync(0xffffffffu, valid ? s[u] : (0xFFFFFF00u | (uint32_t)lane));
+      lead[u] = valid && lane == __ffs(grp) - 1;
+      fix[u] = valid ? xf_fix_of(l[u]) : 0ll;
+      if (__any_sync(0xffffffffu, valid && __popc(grp) > 1)) {
+        long long sum = 0ll;
+        for (int b = 0; b < 32; ++b) {
+          const long long o = __shfl_sync(0xffffffffu, fix[u], b);
+          if ((grp >> b) & 1u) sum += o;
+        }
+        fix[u] = sum;
       }
-      fix = sum;
+      issued[u] = false;
+      q2n[u] = q2[u]; o2[u] = q2[u]; o3[u] = q3[u];
+      reload[u] = lead[u] && have_stash && (q3[u] & XF_TAG_MASK) == XF_TAG_MASK;  // the Pull saw an imported weight
+      if (lead[u] && !reload[u]) {
+        xf_lazy_fold(t, q1[u], q2[u], q3[u], seq, q2n[u]);
+        issued[u] = xf_lazy_deposit_issue(xf_row(t, s[u]), q2[u], q3[u], q2n[u], seq, fix[u], o2[u], o3[u]);
+      }
     }
-    if (lead) {
-      uint64_t q2n;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!lead[u]) continue;
+      uint8_t* rowp = xf_row(t, s[u]);
       bool stale = false;
-      xf_lazy_fold(t, q1, q2, q3, seq, q2n);
-      if (xf_lazy_deposit(t, rowp, q2, q3, q2n, seq, fix, stash != nullptr ? &stale : nullptr)) ++open_acc;
+      if (!reload[u] &&
+          xf_lazy_deposit_resolve(t, rowp, issued[u], q2[u], q3[u], o2[u], o3[u], seq, fix[u], have_stash ? &stale : nullptr))
+        ++open_acc;
       if (stale) {
-        // an earlier source of this round changed the row since the Pull: take a fresh look
+        // An earlier source of this round changed the row since the Pull.  The failed CAS has brought the row's
+        // current state words back; rows with an imported weight never come this way (marked by the Pull), so
+        // bytes 8..15 play no part and no further look at the row is needed.
+        uint64_t r2n;
+        xf_lazy_fold(t, 0ull, o2[u], o3[u], seq, r2n);
+        if (xf_lazy_deposit(t, rowp, o2[u], o3[u], r2n, seq, fix[u])) ++open_acc;
+      } else if (reload[u]) {
         const XfHead h = xf_load_head(rowp);
-        q2 = xf_raw_q2(h);
-        q3 = xf_raw_q3(h);
-        xf_lazy_fold(t, xf_raw_q1(h), q2, q3, seq, q2n);
-        if (xf_lazy_deposit(t, rowp, q2, q3, q2n, seq, fix)) ++open_acc;
+        uint64_t r2n;
+        xf_lazy_fold(t, xf_raw_q1(h), xf_raw_q2(h), xf_raw_q3(h), seq, r2n);
+        if (xf_lazy_deposit(t, rowp, xf_raw_q2(h), xf_raw_q3(h), r2n, seq, fix[u])) ++open_acc;
       }
     }
   }
+#undef XF_PUSH_FETCH
   if (open_acc) atomicAdd(&s_open, open_acc);
   __syncthreads();
   if (threadIdx.x == 0 && s_open && uniq_remote) atomicAdd_system(uniq_remote, (unsigned long long)s_open);

@@ -341,8 +341,12 @@ __device__ __forceinline__ uint64_t xf_raw_q3(const XfHead& h) {
   return (uint64_t)__float_as_uint(h.z) | ((uint64_t)h.flags << 32);
 }
 __device__ __forceinline__ uint64_t xf_raw_q1(const XfHead& h) { return (uint64_t)__double_as_longlong(h.g); }
-// digest of a lazy row's state word that validates an imported weight kept in bytes 8..15 (never 0 for q2 == 0)
-__device__ __forceinline__ uint32_t xf_lazy_check(uint64_t q2) { return (uint32_t)q2 ^ (uint32_t)(q2 >> 32) ^ 0xA5A5A5A5u; }
+// digest of a lazy row's state word that validates an imported weight kept in bytes 8..15; never 0, so a row
+// without an imported weight (bytes 8..15 all zero) can never pass for one, whatever its state
+__device__ __forceinline__ uint32_t xf_lazy_check(uint64_t q2) {
+  const uint32_t c = (uint32_t)q2 ^ (uint32_t)(q2 >> 32) ^ 0xA5A5A5A5u;
+  return c ? c : 1u;
+}
 // What batch `seq` pulls from a lazy row whose second half is (q2, q3): the weight with the pending optimizer
 // step (the Push of the batch named by the tag, gradient = (float)(residual sum) / rows, lr_worker.cc:116-118)
 // applied.  q2_new = the first word the row gets when it is opened (its state after that step).  Pure.
@@ -430,6 +434,32 @@ __device__ __forceinline__ void xf_lazy_add(uint8_t* rowp, long long fix) {
 // batch: the unique-key count).  *stale (optional): the caller's look may be OLDER than this batch (the sharded
 // owner works from the look its Pull took); a row that meanwhile moved on to another batch is then reported
 // instead of flagged as an error, and the caller looks again.
+// The same in two halves, for callers that keep several deposits in flight: _issue sends the CAS (or, for a row
+// already seen open, the RED) and returns what came back; _resolve acts on it.
+__device__ __forceinline__ bool xf_lazy_deposit_issue(uint8_t* rowp, uint64_t q2, uint64_t q3, uint64_t q2_new, uint32_t seq,
+                                                      long long fix, uint64_t& o2, uint64_t& o3) {
+  if ((uint32_t)(q3 & XF_TAG_MASK) == seq) {  // already open for this batch: nothing comes back
+    xf_lazy_add(rowp, fix);
+    o2 = q2; o3 = q3;
+    return false;
+  }
+  xf_cas128(rowp + XF_OFF_STATE, q2, q3, q2_new, ((unsigned long long)fix << 16) | (uint64_t)seq, o2, o3);
+  return true;
+}
+// returns true when the issued CAS opened the row; *stale as in xf_lazy_deposit
+__device__ __forceinline__ bool xf_lazy_deposit_resolve(const XfTableView& t, uint8_t* rowp, bool issued, uint64_t q2, uint64_t q3,
+                                                        uint64_t o2, uint64_t o3, uint32_t seq, long long fix, bool* stale) {
+  if (stale) *stale = false;
+  if (!issued) return false;
+  if (o2 == q2 && o3 == q3) return true;
+  if ((uint32_t)(o3 & XF_TAG_MASK) == seq) {  // another token of this batch was first
+    xf_lazy_add(rowp, fix);
+    return false;
+  }
+  if (stale) *stale = true;
+  else *t.error = 2;
+  return false;
+}
 __device__ __forceinline__ bool xf_lazy_deposit(const XfTableView& t, uint8_t* rowp, uint64_t q2, uint64_t q3, uint64_t q2_new,
                                                 uint32_t seq, long long fix, bool* stale = nullptr) {
   if (stale) *stale = false;
