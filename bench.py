@@ -262,19 +262,22 @@ def text_leg(api, tr, wl, rank, steps, warm, barrier):
         assert rc == 0, lib.xf_last_error()
 
     # ---- (a) from the file: loader forms the block (two alternating page-locked buffers), rewound per epoch
-    def run_file(n):
-        check(lib.xf_loader_rewind(ld.h))
+    def next_block():
+        check(lib.xf_loader_rewind(ld.h))   # the same shard again
         check(lib.xf_loader_next_raw(ld.h, C.byref(text), C.byref(ln)))
         check(lib.xf_trainer_ingest_begin(tr.h, text, ln.value))
+
+    # Both variants keep TWO blocks in flight behind the one being trained on (include/xflow_b200.h,
+    # xf_trainer_ingest_begin): H2D of block i+2, parse of block i+1 and the step of block i run at the same time.
+    def run_file(n):
+        for i in range(min(n, 2)):
+            next_block()
         for i in range(n):
-            if i + 1 < n:   # read the next block (the same shard again) while the device parses this one
-                check(lib.xf_loader_rewind(ld.h))
-                check(lib.xf_loader_next_raw(ld.h, C.byref(text), C.byref(ln)))
             check(lib.xf_trainer_ingest_end(tr.h, C.byref(r), C.byref(z)))
             assert r.value == B_ROWS
             check(lib.xf_trainer_step_ingested(tr.h, 0, r.value))
-            if i + 1 < n:
-                check(lib.xf_trainer_ingest_begin(tr.h, text, ln.value))
+            if i + 2 < n:   # the loader's buffer of block i is free again: its copy finished before _end(i) returned
+                next_block()
     # ---- (b) text already in page-locked host memory (two copies, alternated like a reader would)
     bufs = []
     for _ in range(2):
@@ -284,13 +287,14 @@ def text_leg(api, tr, wl, rank, steps, warm, barrier):
         bufs.append(p)
 
     def run_pinned(n):
-        check(lib.xf_trainer_ingest_begin(tr.h, bufs[0], size))
+        for i in range(min(n, 2)):
+            check(lib.xf_trainer_ingest_begin(tr.h, bufs[i & 1], size))
         for i in range(n):
             check(lib.xf_trainer_ingest_end(tr.h, C.byref(r), C.byref(z)))
             assert r.value == B_ROWS
             check(lib.xf_trainer_step_ingested(tr.h, 0, r.value))
-            if i + 1 < n:
-                check(lib.xf_trainer_ingest_begin(tr.h, bufs[(i + 1) & 1], size))
+            if i + 2 < n:
+                check(lib.xf_trainer_ingest_begin(tr.h, bufs[i & 1], size))
     out = {"text_bytes_per_step": size}
     for name, fn in (("file", run_file), ("pinned", run_pinned)):
         fn(warm)
@@ -422,7 +426,7 @@ def run_workload(name, wl, args, rank, world, local, comm, api, torch, stream, s
                       "text_gbs_per_gpu": text["text_bytes_per_step"] / t / 1e9,
                       "api": "xf_trainer_ingest_begin / _end + xf_trainer_step_ingested (C ABI): the batch as TEXT in the "
                              "reference's format in page-locked host memory -> H2D of the raw text -> parse + hash + step on "
-                             "the device; block i+1 is copied and parsed while block i trains",
+                             "the device; block i+2 is copied and block i+1 parsed while block i trains",
                       "from_file": {"value": world * B / tf, "unit": "examples/s", "ms_per_step": tf * 1e3,
                                     "api": "the same with xf_loader_next_raw forming each block from the text shard in the page "
                                            "cache (what the reference's fread + parser do per epoch)"},

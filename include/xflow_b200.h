@@ -214,7 +214,11 @@ XF_DLL int xf_trainer_ingest_text(xf_trainer* tr, const char* text, uint64_t len
  * the trainer's ingest stream (two device-side block buffers) and returns at once; `text` must stay untouched
  * until _end returns (page-locked memory is copied by DMA, pageable memory is staged first).  _end waits for
  * that parse only — not for training steps still running on the previous block — and makes the block
- * current.  One block may be in flight. */
+ * current.  Up to TWO blocks may be outstanding: the second _begin copies its text at once (into the buffer of
+ * the block being trained on, whose text is no longer needed) and its parse is launched by the _end that
+ * retires that block, so that with  begin(i+2); step(i); end(i+1)  the H2D of one block runs beside the parse
+ * of the previous one and the training step of the one before.  _end always completes the OLDEST outstanding
+ * block.  If _end fails (malformed or oversized block) every outstanding block is dropped. */
 XF_DLL int xf_trainer_ingest_begin(xf_trainer* tr, const char* text, uint64_t len);
 XF_DLL int xf_trainer_ingest_end(xf_trainer* tr, uint32_t* rows, uint32_t* nnz);
 XF_DLL int xf_trainer_step_ingested(xf_trainer* tr, uint32_t row_start, uint32_t row_end);

@@ -87,7 +87,6 @@ def test_two_phase_ingest_pipeline_equals_one_shot(trainer, tmp_path):
     text, ln, r, z = C.c_void_p(), C.c_uint64(), C.c_uint32(), C.c_uint32()
     assert lib.xf_loader_next_raw(ld.h, C.byref(text), C.byref(ln)) == 0
     assert lib.xf_trainer_ingest_begin(trainer.h, text, ln.value) == 0
-    assert lib.xf_trainer_ingest_begin(trainer.h, text, ln.value) != 0      # one block in flight at most
     got = []
     while True:
         nt, nl = C.c_void_p(), C.c_uint64()
@@ -101,6 +100,55 @@ def test_two_phase_ingest_pipeline_equals_one_shot(trainer, tmp_path):
             break
     assert lib.xf_trainer_ingest_end(trainer.h, C.byref(r), C.byref(z)) != 0  # nothing in flight
     _same_blocks(want, got)
+
+
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "page-locked"])
+def test_two_blocks_in_flight(trainer, tmp_path, pinned):
+    """Depth 2: begin(i+2); step(i); end(i+1).  The second outstanding block's text is copied into the buffer of
+    the block being trained on, its parse is launched by the _end that retires that block; a third _begin is
+    refused; every block arrives exactly as the synchronous call delivers it, and in order."""
+    import ctypes as C
+    row_ptr, ids, labels = datagen.make_ids(6, 7000, 20, 1 << 30, ragged=True)
+    path = str(tmp_path / "pipe2-00000")
+    datagen.write_text(path, row_ptr, ids, labels)
+    want = _blocks_device(path, 1 << 16, trainer)
+    assert len(want) > 6
+    lib = api.lib()
+    ld = api.Loader(path, 1 << 16)
+    text, ln, r, z = C.c_void_p(), C.c_uint64(), C.c_uint32(), C.c_uint32()
+    blocks, keep = [], []
+    while True:
+        assert lib.xf_loader_next_raw(ld.h, C.byref(text), C.byref(ln)) == 0
+        if not ln.value:
+            break
+        raw = C.string_at(text, ln.value)
+        if pinned:
+            p = C.c_void_p()
+            assert lib.xf_host_alloc(C.byref(p), len(raw) + 16) == 0
+            C.memmove(p, raw, len(raw))
+            blocks.append((p, len(raw)))
+        else:
+            keep.append(raw)
+            blocks.append((C.c_char_p(raw), len(raw)))
+    n = len(blocks)
+    assert n == len(want)
+    assert lib.xf_trainer_ingest_begin(trainer.h, blocks[0][0], blocks[0][1]) == 0
+    assert lib.xf_trainer_ingest_begin(trainer.h, blocks[1][0], blocks[1][1]) == 0
+    assert lib.xf_trainer_ingest_begin(trainer.h, blocks[2][0], blocks[2][1]) != 0      # two outstanding at most
+    assert lib.xf_trainer_ingest_text(trainer.h, blocks[2][0], blocks[2][1], C.byref(r), C.byref(z)) != 0
+    got = []
+    for i in range(n):
+        assert lib.xf_trainer_ingest_end(trainer.h, C.byref(r), C.byref(z)) == 0, lib.xf_last_error()
+        trainer.step_ingested(0, r.value)                                    # asynchronous
+        if i + 2 < n:
+            assert lib.xf_trainer_ingest_begin(trainer.h, blocks[i + 2][0], blocks[i + 2][1]) == 0, lib.xf_last_error()
+        got.append(trainer.ingested_export(r.value, z.value))               # block i, while i+1 parses and i+2 arrives
+    assert lib.xf_trainer_ingest_end(trainer.h, C.byref(r), C.byref(z)) != 0  # nothing outstanding
+    _same_blocks(want, got)
+    if pinned:
+        trainer.sync()
+        for p, _ in blocks:
+            lib.xf_host_free(p)
 
 
 def test_synthetic_ragged_multi_block(trainer, tmp_path):

@@ -644,7 +644,9 @@ XF_DLL int xf_trainer_create(xf_trainer** out, xf_table* table, xf_comm* comm, c
   tr->cfg = *cfg;
   XF_CUDA_TRY(cudaStreamCreateWithFlags(&tr->copy_stream, cudaStreamNonBlocking));
   XF_CUDA_TRY(cudaStreamCreateWithFlags(&tr->ing_stream, cudaStreamNonBlocking));
+  XF_CUDA_TRY(cudaStreamCreateWithFlags(&tr->ing_copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
+    XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->ing[i].copied, cudaEventDisableTiming));
     XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->ing[i].parsed, cudaEventDisableTiming));
     XF_CUDA_TRY(cudaEventCreateWithFlags(&tr->ing[i].consumed, cudaEventDisableTiming));
     XF_CUDA_TRY(cudaHostAlloc(&tr->ing[i].h_totals, 16, cudaHostAllocDefault));
@@ -693,9 +695,11 @@ XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
     cudaEventDestroy(b.copied); cudaEventDestroy(b.consumed); cudaEventDestroy(b.staged);
   }
   tr->touched.release(); tr->loss.release(); tr->pctr.release();
+  cudaStreamSynchronize(tr->ing_copy_stream);
   cudaStreamSynchronize(tr->ing_stream);
   for (int i = 0; i < 2; ++i) {
     xf_trainer::IngestSet& g = tr->ing[i];
+    if (g.copied) cudaEventDestroy(g.copied);
     g.text.release(); g.row_ptr.release(); g.keys.release(); g.labels.release(); g.totals.release(); g.stage.release();
     if (g.h_totals) cudaFreeHost(g.h_totals);
     if (g.parsed) cudaEventDestroy(g.parsed);
@@ -703,6 +707,7 @@ XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
   }
   tr->ing_scratch.release();
   cudaStreamDestroy(tr->ing_stream);
+  cudaStreamDestroy(tr->ing_copy_stream);
   cudaFree(tr->d_unique_total); cudaFree(tr->d_abs_loss);
   cudaFreeHost(tr->h_abs_loss);
   cudaStreamDestroy(tr->copy_stream);
@@ -1091,35 +1096,28 @@ XF_DLL int xf_trainer_step_host_ids_async(xf_trainer* tr, const uint32_t* row_pt
   return XF_OK;
 }
 
-// Two-phase ingest.  _begin copies the block to the device and parses it on the trainer's ingest stream
+// Two-phase ingest.  _begin copies the block to the device and parses it on the trainer's ingest streams
 // into the set that is NOT being trained on, and returns at once; _end waits for that parse only, makes
-// the set current and reports its size.  A caller that reads block i+1 from disk between _begin(i+1)... see
-// WorkerBase::batch_training (worker.cc): read, H2D, parse of block i+1 overlap the step of block i.
-XF_DLL int xf_trainer_ingest_begin(xf_trainer* tr, const char* text, uint64_t len) {
-  if (!tr || (!text && len)) return XF_ERR_ARG;
-  if (tr->ing_pending) { xf_set_error("ingest: xf_trainer_ingest_begin called twice without xf_trainer_ingest_end"); return XF_ERR_STATE; }
-  if (len >= 0xFFFFFFF0ull) { xf_set_error("ingest: a block must be smaller than 4 GiB (u32 token offsets)"); return XF_ERR_ARG; }
-  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
-  xf_trainer::IngestSet& g = tr->ing[tr->ing_cur ^ 1];
+// the set current and reports its size: read, H2D and parse of block i+1 overlap the step of block i
+// (WorkerBase::run_blocks, worker.cc).
+// A SECOND _begin may be issued before the first one's _end.  It targets the set that is being trained on:
+// its text buffer is free (only the parsed arrays are read by the steps), so the copy starts at once on the
+// copy stream and runs beside the first block's parse; its parse is launched by the _end that retires the
+// set.  With the loop  begin(i+2); step(i); end(i+1)  the H2D of one block, the parse of the previous one and
+// the training step of the one before that all run at the same time.
+static int xf_ingest_launch_parse(xf_trainer* tr, xf_trainer::IngestSet& g) {
   cudaStream_t is = tr->ing_stream;
   // the steps that read this set (two blocks ago) must have finished before it is overwritten
   XF_CUDA_TRY(cudaStreamWaitEvent(is, g.consumed, 0));
+  XF_CUDA_TRY(cudaStreamWaitEvent(is, g.copied, 0));
+  const uint64_t len = g.len;
   // upper bounds for a block of `len` bytes: shortest row "0\n" = 2 bytes, shortest token "a:b:c " ~ 4 bytes
   g.max_rows = (uint32_t)std::min<uint64_t>(len / 2 + 2, tr->cfg.max_rows);
   g.max_tok = (uint32_t)std::min<uint64_t>(len / 4 + 2, tr->cfg.max_nnz);
-  XF_TRY(g.text.ensure(len + 16));
   XF_TRY(g.row_ptr.ensure(((size_t)g.max_rows + 2) * 4));
   XF_TRY(g.keys.ensure(((size_t)g.max_tok + 1) * 8));
   XF_TRY(g.labels.ensure((size_t)g.max_rows + 1));
   XF_TRY(g.totals.ensure(16));
-  const void* src = text;
-  if (len && !xf_is_pinned(text)) {
-    XF_CUDA_TRY(cudaEventSynchronize(g.parsed));  // the stage may still be the source of this set's previous H2D
-    XF_TRY(g.stage.ensure(len));
-    memcpy(g.stage.p, text, len);
-    src = g.stage.p;
-  }
-  if (len) XF_CUDA_TRY(cudaMemcpyAsync(g.text.p, src, len, cudaMemcpyHostToDevice, is));
   // totals = {rows, tokens, parse error}; the parser's error word is its own, not the table's sticky one
   XF_CUDA_TRY(cudaMemsetAsync(g.totals.p, 0, 16, is));
   XF_TRY(xf_launch_parse(g.text.as<char>(), len, tr->ing_scratch, g.row_ptr.as<uint32_t>(), g.keys.as<uint64_t>(),
@@ -1127,24 +1125,56 @@ XF_DLL int xf_trainer_ingest_begin(xf_trainer* tr, const char* text, uint64_t le
   tr->launches += 5;
   XF_CUDA_TRY(cudaMemcpyAsync(g.h_totals, g.totals.p, 12, cudaMemcpyDeviceToHost, is));
   XF_CUDA_TRY(cudaEventRecord(g.parsed, is));
-  tr->ing_pending = true;
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_ingest_begin(xf_trainer* tr, const char* text, uint64_t len) {
+  if (!tr || (!text && len)) return XF_ERR_ARG;
+  if (tr->ing_pending >= 2) { xf_set_error("ingest: at most two xf_trainer_ingest_begin calls may be outstanding"); return XF_ERR_STATE; }
+  if (len >= 0xFFFFFFF0ull) { xf_set_error("ingest: a block must be smaller than 4 GiB (u32 token offsets)"); return XF_ERR_ARG; }
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  // first outstanding block -> the idle set; second -> the set being trained on (text only, for now)
+  xf_trainer::IngestSet& g = tr->ing[tr->ing_pending == 0 ? (tr->ing_cur ^ 1) : tr->ing_cur];
+  // the set's previous text was consumed by its parse, which the _end that made the set current (or retired it)
+  // has waited for; a set that was never used has nothing outstanding
+  XF_CUDA_TRY(cudaEventSynchronize(g.parsed));
+  XF_TRY(g.text.ensure(len + 16));
+  const void* src = text;
+  if (len && !xf_is_pinned(text)) {
+    XF_TRY(g.stage.ensure(len));
+    memcpy(g.stage.p, text, len);
+    src = g.stage.p;
+  }
+  if (len) XF_CUDA_TRY(cudaMemcpyAsync(g.text.p, src, len, cudaMemcpyHostToDevice, tr->ing_copy_stream));
+  XF_CUDA_TRY(cudaEventRecord(g.copied, tr->ing_copy_stream));
+  g.len = len;
+  if (tr->ing_pending == 0) XF_TRY(xf_ingest_launch_parse(tr, g));
+  ++tr->ing_pending;
   return XF_OK;
 }
 
 XF_DLL int xf_trainer_ingest_end(xf_trainer* tr, uint32_t* rows, uint32_t* nnz) {
   if (!tr || !rows || !nnz) return XF_ERR_ARG;
-  if (!tr->ing_pending) { xf_set_error("ingest: xf_trainer_ingest_end without xf_trainer_ingest_begin"); return XF_ERR_STATE; }
+  if (tr->ing_pending == 0) { xf_set_error("ingest: xf_trainer_ingest_end without xf_trainer_ingest_begin"); return XF_ERR_STATE; }
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
   xf_trainer::IngestSet& g = tr->ing[tr->ing_cur ^ 1];
-  tr->ing_pending = false;
+  --tr->ing_pending;
   XF_CUDA_TRY(cudaEventSynchronize(g.parsed));
   const uint32_t* tot = g.h_totals;
   const int e = (int)tot[2];
   g.rows = g.nnz = 0;
-  if (e == 4) { xf_set_error("ingest: token without three ':'-separated fields"); return XF_ERR_IO; }
-  if (e == 3 || tot[0] > g.max_rows || tot[1] > g.max_tok) {
+  int rc = XF_OK;
+  if (e == 4) { xf_set_error("ingest: token without three ':'-separated fields"); rc = XF_ERR_IO; }
+  else if (e == 3 || tot[0] > g.max_rows || tot[1] > g.max_tok) {
     xf_set_error("ingest: block (%u rows, %u tokens) exceeds trainer limits (%u, %u)", tot[0], tot[1],
                  tr->cfg.max_rows, tr->cfg.max_nnz);
-    return XF_ERR_ARG;
+    rc = XF_ERR_ARG;
+  }
+  if (rc != XF_OK) {
+    // the failed block is dropped; a second outstanding block (text already copied into the current set) becomes
+    // the first: it cannot be parsed there, so it is dropped as well and the caller starts over
+    if (tr->ing_pending) { cudaStreamSynchronize(tr->ing_copy_stream); tr->ing_pending = 0; }
+    return rc;
   }
   g.rows = tot[0];
   g.nnz = tot[1];
@@ -1155,11 +1185,15 @@ XF_DLL int xf_trainer_ingest_end(xf_trainer* tr, uint32_t* rows, uint32_t* nnz) 
   XF_CUDA_TRY(cudaStreamWaitEvent(tr->table->stream, g.parsed, 0));
   *rows = g.rows;
   *nnz = g.nnz;
+  // the set that was current until now is retired (the caller has issued its last step on it): a second
+  // outstanding block, whose text is already on its way into that set, can be parsed there now
+  if (tr->ing_pending) XF_TRY(xf_ingest_launch_parse(tr, tr->ing[tr->ing_cur ^ 1]));
   return XF_OK;
 }
 
 XF_DLL int xf_trainer_ingest_text(xf_trainer* tr, const char* text, uint64_t len, uint32_t* rows, uint32_t* nnz) {
   if (!tr || (!text && len) || !rows || !nnz) return XF_ERR_ARG;
+  if (tr->ing_pending) { xf_set_error("ingest: xf_trainer_ingest_text while a two-phase ingest is outstanding"); return XF_ERR_STATE; }
   tr->ing_rows = tr->ing_nnz = 0;
   XF_TRY(xf_trainer_ingest_begin(tr, text, len));
   return xf_trainer_ingest_end(tr, rows, nnz);

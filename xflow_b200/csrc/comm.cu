@@ -322,8 +322,13 @@ int xf_mg_create(xf_trainer* tr) {
     if (cudaMemsetAsync(mg->slab, 0, mg->L.off_in_keys, st) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&mg->st2, cudaStreamNonBlocking, lo) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
-    if (cudaStreamCreateWithFlags(&mg->st3, cudaStreamNonBlocking) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
+    // Routing and the DONE signal are what the OTHER ranks wait for.  Giving their streams the high priority
+    // (XFLOW_MG_ROUTE_PRIO=1) was measured at 2 GPUs: 163.6 M examples/s against 166.7 M at equal priority, twice
+    // each, so equal priority stays the default.
+    const char* rp = getenv("XFLOW_MG_ROUTE_PRIO");
+    const int prio = (rp && *rp == '1') ? hi : lo;
+    if (cudaStreamCreateWithPriority(&mg->st2, cudaStreamNonBlocking, prio) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
+    if (cudaStreamCreateWithPriority(&mg->st3, cudaStreamNonBlocking, prio) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
     if (cudaEventCreateWithFlags(&mg->ev_meta, cudaEventDisableTiming) != cudaSuccess) { rc = XF_ERR_CUDA; break; }
     if ((rc = mg->slots.ensure((size_t)S * mg->cap * 4)) != XF_OK) break;
     if ((rc = mg->rowv_local.ensure((size_t)mg->max_rows * 8 + 16)) != XF_OK) break;

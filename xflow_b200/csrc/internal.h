@@ -110,14 +110,19 @@ struct xf_trainer {
     XfPinBuf stage;                 // page-locked copy of a pageable source
     uint32_t* h_totals = nullptr;   // pinned {rows, tokens, parse error}
     cudaEvent_t parsed = nullptr;   // H2D + parse of this set finished (ingest stream)
+    cudaEvent_t copied = nullptr;   // the block's text has arrived in `text` (ingest copy stream)
+    uint64_t len = 0;               // bytes of the block whose text is in `text`
     cudaEvent_t consumed = nullptr; // the last step that reads this set finished (table stream)
     uint32_t rows = 0, nnz = 0, max_rows = 0, max_tok = 0;
   };
   IngestSet ing[2];
   XfDevBuf ing_scratch;
-  cudaStream_t ing_stream = nullptr;
+  cudaStream_t ing_stream = nullptr;       // parses
+  cudaStream_t ing_copy_stream = nullptr;  // H2D of the blocks' text: the copy of block i+2 runs beside the parse of i+1
   int ing_cur = 0;                  // the set xf_trainer_step_ingested works on
-  bool ing_pending = false;         // xf_trainer_ingest_begin issued, _end not yet called
+  int ing_pending = 0;              // xf_trainer_ingest_begin calls not yet matched by _end (0..2); the second one
+                                    // targets the set being trained: its text is copied at once, its parse is
+                                    // launched by the _end that frees the set
   uint32_t ing_rows = 0, ing_nnz = 0;
   void* mg = nullptr;                   // multi-GPU exchange state (comm.cu)
   cudaEvent_t input_ready = nullptr;    // set by the host-batch paths: H2D of the batch about to be stepped
