@@ -91,11 +91,13 @@ XF_DLL int xf_table_destroy(xf_table* t);
 XF_DLL int xf_table_pull(xf_table* t, const uint64_t* keys, uint64_t n, float* w_out, float* v_out);
 
 /* replaces: KVWorker<float>::Push + Wait (kv_app.h:110-118) served by the handles' push branch
- * (ftrl.h:54-74,112-141 ; sgd.h:46-52,90-96).  keys must be unique.  gw: n floats or NULL (app 0);
- * gv: n*K floats or NULL (app 1). */
+ * (ftrl.h:54-74,112-141 ; sgd.h:46-52,90-96).  keys must be unique, in any order (KVWorker::Push takes them
+ * sorted and unique; a repeated key is refused with XF_ERR_ARG before anything is applied).  gw: n floats or
+ * NULL (app 0); gv: n*K floats or NULL (app 1). */
 XF_DLL int xf_table_push(xf_table* t, const uint64_t* keys, uint64_t n, const float* gw, const float* gv);
 
-/* same two operations on DEVICE pointers, asynchronous on the table's stream (no host sync) */
+/* same two operations on DEVICE pointers, asynchronous on the table's stream (no host sync).  The device push
+ * does not look for repeated keys (that would take a sort): unique keys are the caller's contract there. */
 XF_DLL int xf_table_pull_device(xf_table* t, const uint64_t* d_keys, uint64_t n, float* d_w_out, float* d_v_out);
 XF_DLL int xf_table_push_device(xf_table* t, const uint64_t* d_keys, uint64_t n, const float* d_gw, const float* d_gv);
 

@@ -567,3 +567,21 @@ def test_canonical_fm_with_values_matches_float64_model(K, opt):
     # a canonical table refuses the reference-shaped models and vice versa
     with pytest.raises(api.XflowError):
         api.Trainer(t, model=api.MODEL_FM, max_rows=B, max_nnz=B * d)
+
+
+def test_push_refuses_repeated_keys():
+    """KVWorker::Push takes unique keys; a repeated key would be two unordered updates of one row.  The host
+    entry point refuses it (sorted or not) before anything is applied."""
+    t = api.Table(latent_dim=0, optimizer=api.OPT_FTRL, capacity=1 << 12)
+    keys = np.array([5, 9, 11], np.uint64)
+    t.push(keys, gw=np.ones(3, np.float32))
+    before = t.export(keys)
+    for bad in (np.array([5, 9, 9, 11], np.uint64), np.array([11, 5, 9, 5], np.uint64)):
+        rc = api.lib().xf_table_push(t.h, bad.ctypes.data_as(api.C.c_void_p), bad.size,
+                                     np.ones(bad.size, np.float32).ctypes.data_as(api.C.c_void_p), None)
+        assert rc != 0 and b"more than once" in api.lib().xf_last_error()
+    after = t.export(keys)
+    for k in ("w", "nw", "zw"):
+        assert np.array_equal(before[k], after[k])
+    t.push(np.array([11, 5, 9], np.uint64), gw=np.ones(3, np.float32))      # unsorted but unique: fine
+    t.close()

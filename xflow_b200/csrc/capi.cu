@@ -384,10 +384,35 @@ XF_DLL int xf_table_pull(xf_table* t, const uint64_t* keys, uint64_t n, float* w
   return xf_table_sync(t);
 }
 
+// KVWorker::Push takes sorted, unique keys (ps-lite kv_app.h: "keys must be unique and sorted in increasing order").
+// The update kernel gives every list entry its own warp lanes: the same key twice would be two unordered
+// read-modify-writes of one row.  Sorted input costs one pass; anything else is checked on a sorted copy.
+static int xf_check_unique_keys(const uint64_t* keys, uint64_t n) {
+  bool increasing = true;
+  for (uint64_t i = 1; i < n; ++i) {
+    if (keys[i] > keys[i - 1]) continue;
+    if (keys[i] == keys[i - 1]) { xf_set_error("push: key %llu occurs more than once", (unsigned long long)keys[i]); return XF_ERR_ARG; }
+    increasing = false;
+    break;
+  }
+  if (increasing) return XF_OK;
+  try {
+    std::vector<uint64_t> c(keys, keys + n);
+    std::sort(c.begin(), c.end());
+    const auto dup = std::adjacent_find(c.begin(), c.end());
+    if (dup != c.end()) { xf_set_error("push: key %llu occurs more than once", (unsigned long long)*dup); return XF_ERR_ARG; }
+  } catch (const std::exception&) {
+    xf_set_error("push: out of host memory while checking %llu keys", (unsigned long long)n);
+    return XF_ERR_IO;
+  }
+  return XF_OK;
+}
+
 XF_DLL int xf_table_push(xf_table* t, const uint64_t* keys, uint64_t n, const float* gw, const float* gv) {
   if (!t || (!keys && n)) return XF_ERR_ARG;
   std::lock_guard<std::mutex> host_lock(t->host_mu);
   if (n == 0) return XF_OK;
+  XF_TRY(xf_check_unique_keys(keys, n));
   XF_CUDA_TRY(cudaSetDevice(t->cfg.device));
   const int K = t->view.K;
   XF_TRY(t->s_keys.ensure(n * 8));
