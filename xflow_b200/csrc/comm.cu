@@ -20,7 +20,7 @@
 //                                              wait  ROWV >= t from all sources
 //                                              for s in 0..S-1:  push kernel(s) of source s  (Push handler,
 //                                                   one optimizer step per (source, key), rank order)
-//                                              signal DONE = t
+//   side stream (after the pushes): token-count readback for the growth checks, then signal DONE = t
 //
 // Semantics = one legal schedule of the reference's asynchronous run: every worker pulls before any push
 // of the round, pushes land in rank order (tests/test_gpu_multi.py against the oracle's lock-step run).
