@@ -42,7 +42,8 @@ enum {
 };
 
 enum { XF_MODEL_LR = 0, XF_MODEL_FM = 1,              /* main.cc:26-39: '0' = LR, '1' = FM */
-       XF_MODEL_FM_CANONICAL = 2 };                   /* NOT the reference's model: the textbook FM, see below */
+       XF_MODEL_FM_CANONICAL = 2,                     /* NOT the reference's model: the textbook FM, see below */
+       XF_MODEL_MVM = 3 };                            /* a DEFINED multi-view machine (mvm_worker.cc is not), see below */
 enum { XF_OPTIMIZER_FTRL = 0, XF_OPTIMIZER_SGD = 1 }; /* server.h:24-29 (comment toggle in the reference) */
 enum {
   XF_VINIT_DEFAULT = 0,  /* FTRL: N(0,1)*1e-2 (ftrl.h:114-120, counter-based here); SGD: 0.001 (sgd.h:68-70) */
@@ -74,7 +75,7 @@ typedef struct xf_table_config {
   uint64_t capacity;     /* initial slot count (rounded up to a power of two); 0 = 1<<20.  Grows on demand. */
   int shard_index;       /* this table owns keys of shard_index out of num_shards (postoffice.cc:134-143) */
   int num_shards;        /* 1 = whole key space */
-  int canonical_fm;      /* 1: rows carry the accumulators of XF_MODEL_FM_CANONICAL (latent_dim in {4,8,16,32,64,128}) */
+  int canonical_fm;      /* 1: rows carry the accumulators of XF_MODEL_FM_CANONICAL / XF_MODEL_MVM (latent_dim in {4,8,16,32,64,128}) */
 } xf_table_config;
 
 /* fills *cfg with the reference's compile-time defaults (ftrl.h:15-20, sgd.h:16) */
@@ -179,6 +180,21 @@ XF_DLL int xf_trainer_step_device_values(xf_trainer* tr, const uint32_t* d_row_p
                                          const float* d_vals, const uint8_t* d_labels, uint32_t rows, uint32_t nnz);
 XF_DLL int xf_trainer_predict_host_values(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys, const float* vals,
                                           uint32_t rows, uint32_t nnz, float* pctr_out);
+/* A DEFINED multi-view machine.  src/model/mvm/mvm_worker.cc indexes its per-row field sums one past
+ * their end and multiplies in the sums of fields a row does not have (:43,57,75,86-92,262): its output is not a
+ * function of its input.  This is the model that code is reaching for, over the same table:
+ *     s[f][k] = sum over the row's tokens of field f of v_ik x_i ,   y = sum_k prod_{f present in the row} s[f][k]
+ *     p = sigmoid(y) ,  dL/dv_ik = (p - label) x_i prod_{f' present, f' != field(i)} s[f'][k] ,  gradients / rows, one
+ *     FTRL / SGD step per touched key on v only (no linear term: mvm_worker.cc pulls and pushes v alone).
+ * fields[nnz]: the tokens' field ids (libffm's fgid), each < 32.  vals[nnz] or NULL (all 1).  A row without
+ * tokens predicts sigmoid(0).  Needs XF_MODEL_MVM on a table with canonical_fm = 1 and latent_dim in {4,8,16,32};
+ * single GPU. */
+XF_DLL int xf_trainer_step_host_fields(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys,
+                                       const uint8_t* fields, const float* vals, const uint8_t* labels, uint32_t rows,
+                                       uint32_t nnz, float* mean_abs_loss);
+XF_DLL int xf_trainer_predict_host_fields(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys,
+                                          const uint8_t* fields, const float* vals, uint32_t rows, uint32_t nnz,
+                                          float* pctr_out);
 /* the one-off "init push" of key 0 with zero gradient (lr_worker.cc:180-182, fm_worker.cc:248-252) */
 XF_DLL int xf_trainer_init_push(xf_trainer* tr);
 /* residuals (pctr - label) of the last step; needs keep_loss = 1 */

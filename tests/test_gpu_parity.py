@@ -569,6 +569,81 @@ def test_canonical_fm_with_values_matches_float64_model(K, opt):
         api.Trainer(t, model=api.MODEL_FM, max_rows=B, max_nnz=B * d)
 
 
+@pytest.mark.parametrize("K,opt,with_vals", [(8, "sgd", True), (16, "ftrl", True), (4, "ftrl", False), (32, "sgd", False)])
+def test_defined_mvm_matches_float64_model(K, opt, with_vals):
+    """XF_MODEL_MVM (step_mvm.cu): y = sum_k prod_{fields present} (sum_{tokens of the field} v_k x),
+    gradient of a token = residual * x * product of the OTHER fields' sums, one FTRL / SGD step per touched key on v —
+    against a float64 numpy model of that definition over three steps (the reference's MVMWorker reads past its
+    buffers and has no defined output to compare with)."""
+    gopt, _ = _opt(opt)
+    B, d, space, F = 384, 9, 2500, 5
+    lr = 20.0                                                  # SGD: large enough for the steps to show in float32
+    t = api.Table(latent_dim=K, optimizer=gopt, v_init=api.VINIT_COUNTER, seed=4, canonical_fm=1, learning_rate=lr)
+    tr = api.Trainer(t, model=api.MODEL_MVM, max_rows=B, max_nnz=B * d * 2, keep_loss=True)
+    rng = np.random.default_rng(100 + K)
+    batches = []
+    for step in range(3):
+        rp, keys, lab = datagen.make_csr_keys(170 + step, B, d, space, api.hash_decimal_ids, ragged=(step == 1))
+        fields = rng.integers(0, F, keys.size).astype(np.uint8)
+        if step == 2:
+            fields[: keys.size // 3] = 31                     # the largest admissible field id
+        x = (rng.random(keys.size) * 1.5 + 0.25).astype(np.float32) if with_vals else None
+        if x is not None:
+            x[::5] *= -1.0
+        batches.append((rp, keys, fields, x, lab))
+    allk = np.unique(np.concatenate([b[1] for b in batches]))
+    V0 = rng.normal(0.0, 0.6, (allk.size, K)).astype(np.float32)
+    t.import_(allk, v=V0)
+    V = V0.astype(np.float64); NV = np.zeros_like(V); ZV = np.zeros_like(V)
+    for step, (rp, keys, fields, x, lab) in enumerate(batches):
+        idx = np.searchsorted(allk, keys)
+        row_of = np.repeat(np.arange(B), np.diff(rp).astype(np.int64))
+        x64 = np.ones(keys.size) if x is None else x.astype(np.float64)
+        S = np.zeros((B, 32, K)); np.add.at(S, (row_of, fields.astype(np.int64)), V[idx] * x64[:, None])
+        present = np.zeros((B, 32), bool); present[row_of, fields.astype(np.int64)] = True
+        Sp = np.where(present[:, :, None], S, 1.0)
+        y = np.where(present.any(1), Sp.prod(1).sum(1), 0.0)
+        p = np.where(y < -30, 1e-6, np.where(y > 30, 1.0, np.power(2.718281828, y) / (1 + np.power(2.718281828, y))))
+        loss = p - lab
+        tr.step_host_fields(rp, keys, fields, x, lab)
+        assert_close(tr.get_loss(B), loss, "MVM residuals, step %d" % step, rel=5e-5, abs_floor=5e-6)
+        # product over the other fields of the row, per token
+        excl = np.ones((keys.size, K))
+        for f in range(32):
+            other = present[row_of, f] & (fields != f)
+            excl[other] *= S[row_of[other], f]
+        gtok = loss[row_of, None] * x64[:, None] * excl
+        A = np.zeros_like(V); np.add.at(A, idx, gtok)
+        touched = np.zeros(allk.size, bool); touched[idx] = True
+        g = A / B
+        for i in np.nonzero(touched)[0]:
+            if opt == "ftrl":
+                V[i], NV[i], ZV[i] = _ftrl64(g[i], V[i], NV[i], ZV[i])
+            else:
+                V[i] = V[i] - lr * g[i]
+    e = t.export(allk)
+    assert e["present"].all()
+    if opt == "ftrl":
+        for name, ref in (("v", V), ("nv", NV), ("zv", ZV)):
+            assert_close(e[name].reshape(allk.size, -1), ref, "MVM %s" % name, rel=5e-4, abs_floor=5e-7)
+    else:
+        # what the steps moved, not the (much larger) starting values
+        moved = np.abs(V - V0).max()
+        assert moved > 1e-3
+        assert_close(e["v"].reshape(allk.size, -1) - V0, V - V0, "MVM v - v0", rel=2e-3, abs_floor=2e-6 + 1e-4 * moved)
+    assert not e["w"].any()                                    # no linear term: w is never moved
+    # forward only
+    rp, keys, fields, x, lab = batches[0]
+    got = tr.predict_host_fields(rp, keys, fields, x)
+    assert np.isfinite(got).all() and got.min() >= 0 and got.max() <= 1
+    # field ids the kernel has no room for are refused, and the model needs its field ids
+    bad = fields.copy(); bad[0] = 32
+    with pytest.raises(api.XflowError):
+        tr.step_host_fields(rp, keys, bad, x, lab)
+    with pytest.raises(api.XflowError):
+        tr.step_host(rp, keys, lab)
+
+
 def test_push_refuses_repeated_keys():
     """KVWorker::Push takes unique keys; a repeated key would be two unordered updates of one row.  The host
     entry point refuses it (sorted or not) before anything is applied."""

@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libxflow_b200.so")
 
-MODEL_LR, MODEL_FM, MODEL_FM_CANONICAL = 0, 1, 2
+MODEL_LR, MODEL_FM, MODEL_FM_CANONICAL, MODEL_MVM = 0, 1, 2, 3
 OPT_FTRL, OPT_SGD = 0, 1
 VINIT_DEFAULT, VINIT_COUNTER, VINIT_ZERO = 0, 1, 3
 COMM_ID_BYTES = 128
@@ -69,6 +69,8 @@ SIGNATURES = {
     "xf_trainer_step_host_values": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "xf_trainer_step_device_values": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32]),
     "xf_trainer_predict_host_values": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "xf_trainer_step_host_fields": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "xf_trainer_predict_host_fields": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "xf_trainer_init_push": (_i, [_vp]),
     "xf_trainer_get_loss": (_i, [_vp, _vp, _u32]),
     "xf_trainer_stats": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -393,6 +395,28 @@ class Trainer:
         rows = row_ptr.size - 1
         out = np.empty(rows, np.float32)
         _check(lib().xf_trainer_predict_host_values(self.h, _p(row_ptr), _p(keys), _p(vals), rows, keys.size, _p(out)))
+        return out
+
+    def step_host_fields(self, row_ptr, keys, fields, vals, labels):
+        """One step of the defined multi-view machine (XF_MODEL_MVM): host CSR arrays + the tokens' field ids."""
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint32)
+        keys = np.ascontiguousarray(keys, np.uint64)
+        fields = np.ascontiguousarray(fields, np.uint8)
+        vals = None if vals is None else np.ascontiguousarray(vals, np.float32)
+        labels = np.ascontiguousarray(labels, np.uint8)
+        loss = C.c_float()
+        _check(lib().xf_trainer_step_host_fields(self.h, _p(row_ptr), _p(keys), _p(fields), _p(vals), _p(labels), labels.size,
+                                                 keys.size, C.byref(loss)))
+        return loss.value
+
+    def predict_host_fields(self, row_ptr, keys, fields, vals):
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint32)
+        keys = np.ascontiguousarray(keys, np.uint64)
+        fields = np.ascontiguousarray(fields, np.uint8)
+        vals = None if vals is None else np.ascontiguousarray(vals, np.float32)
+        rows = row_ptr.size - 1
+        out = np.empty(rows, np.float32)
+        _check(lib().xf_trainer_predict_host_fields(self.h, _p(row_ptr), _p(keys), _p(fields), _p(vals), rows, keys.size, _p(out)))
         return out
 
     def step_host_raw(self, row_ptr_addr, keys_addr, labels_addr, rows, nnz, want_loss=True):

@@ -15,7 +15,7 @@ LIBDIR = os.path.join(ROOT, "xflow_b200", "lib")
 LIB = os.path.join(LIBDIR, "libxflow_b200.so")
 OBJDIR = os.path.join(ROOT, "build", "obj")
 
-CU_SOURCES = ["kernels.cu", "step.cu", "step_lazy.cu", "step_fmc.cu", "capi.cu", "comm.cu", "mg_kernels.cu", "ingest.cu", "metric.cu"]
+CU_SOURCES = ["kernels.cu", "step.cu", "step_lazy.cu", "step_fmc.cu", "step_mvm.cu", "capi.cu", "comm.cu", "mg_kernels.cu", "ingest.cu", "metric.cu"]
 CC_SOURCES = ["loader.cc", "metrics.cc", "worker.cc"]
 HEADERS = ["table.cuh", "mg.cuh", "kernels.h", "internal.h", "hash.h", os.path.join(ROOT, "include", "xflow_b200.h"),
            os.path.join(ROOT, "include", "xflow", "xflow.h")]

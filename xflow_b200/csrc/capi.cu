@@ -659,7 +659,14 @@ XF_DLL int xf_trainer_create(xf_trainer** out, xf_table* table, xf_comm* comm, c
     xf_set_error("XF_MODEL_FM_CANONICAL needs a table created with canonical_fm = 1 and no comm");
     return XF_ERR_ARG;
   }
-  if (cfg->model != XF_MODEL_FM_CANONICAL && table->view.canon) { xf_set_error("canonical tables serve XF_MODEL_FM_CANONICAL only"); return XF_ERR_ARG; }
+  if (cfg->model == XF_MODEL_MVM && (!table->view.canon || comm || table->view.K > 32)) {
+    xf_set_error("XF_MODEL_MVM needs a table created with canonical_fm = 1, latent_dim <= 32 and no comm");
+    return XF_ERR_ARG;
+  }
+  if (cfg->model != XF_MODEL_FM_CANONICAL && cfg->model != XF_MODEL_MVM && table->view.canon) {
+    xf_set_error("canonical tables serve XF_MODEL_FM_CANONICAL and XF_MODEL_MVM only");
+    return XF_ERR_ARG;
+  }
   if (cfg->model == XF_MODEL_LR && table->view.K != 0) { xf_set_error("LR needs latent_dim == 0"); return XF_ERR_ARG; }
   if (cfg->max_rows == 0 || cfg->max_nnz == 0) { xf_set_error("max_rows/max_nnz must be > 0"); return XF_ERR_ARG; }
   XF_CUDA_TRY(cudaSetDevice(table->cfg.device));
@@ -715,7 +722,7 @@ XF_DLL int xf_trainer_destroy(xf_trainer* tr) {
   if (tr->mg) xf_mg_destroy(tr);
   for (int i = 0; i < 2; ++i) {
     XfBatchBuf& b = tr->buf[i];
-    b.row_ptr.release(); b.keys.release(); b.labels.release(); b.ids.release(); b.vals.release();
+    b.row_ptr.release(); b.keys.release(); b.labels.release(); b.ids.release(); b.vals.release(); b.fields.release();
     b.h_row_ptr.release(); b.h_keys.release(); b.h_labels.release();
     cudaEventDestroy(b.copied); cudaEventDestroy(b.consumed); cudaEventDestroy(b.staged);
   }
@@ -754,7 +761,7 @@ static int xf_check_batch(xf_trainer* tr, uint32_t rows, uint32_t nnz) {
 // the step proper, on device-resident CSR; mode 0 = train, 1 = predict
 static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys,
                                const uint8_t* d_labels, uint32_t rows, uint32_t nnz, int mode, float* d_abs,
-                               const float* d_vals = nullptr) {
+                               const float* d_vals = nullptr, const uint8_t* d_fields = nullptr) {
   xf_table* t = tr->table;
   if (rows == 0 && !tr->mg) return XF_OK;     // sharded: an empty batch still takes part in the exchange
   if (!tr->mg) XF_TRY(t->ensure_room(nnz));  // the sharded path sizes the shard from what it receives
@@ -788,10 +795,16 @@ static int xf_step_device_impl(xf_trainer* tr, const uint32_t* d_row_ptr, const 
     XF_CUDA_TRY(cudaGetLastError());
     return XF_OK;
   }
-  const bool canon = tr->cfg.model == XF_MODEL_FM_CANONICAL;
+  const bool mvm = tr->cfg.model == XF_MODEL_MVM;
+  const bool canon = tr->cfg.model == XF_MODEL_FM_CANONICAL || mvm;
+  if (mvm && !d_fields && nnz) { xf_set_error("XF_MODEL_MVM steps need the tokens' field ids (xf_trainer_step_host_fields)"); return XF_ERR_ARG; }
   const uint32_t extra = canon ? 0u : xf_step_touched_extra(t->view.K, (int)rows);
   XF_TRY(tr->touched.ensure(((size_t)nnz + extra) * 4));
-  if (canon)
+  if (mvm)
+    xf_launch_step_mvm(t->view, d_row_ptr, d_keys, d_fields, d_vals, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
+                       (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
+                       mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
+  else if (canon)
     xf_launch_step_fmc(t->view, d_row_ptr, d_keys, d_vals, d_labels, (int)rows, mode, tr->touched.as<uint32_t>(),
                        (mode == 0 && tr->cfg.keep_loss) ? tr->loss.as<float>() : nullptr,
                        mode == 1 ? tr->pctr.as<float>() : nullptr, d_abs, st);
@@ -985,6 +998,75 @@ XF_DLL int xf_trainer_predict_host_values(xf_trainer* tr, const uint32_t* row_pt
   XF_TRY(xf_upload_vals(tr, b, vals, nnz, &d_vals));
   XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows, nnz, 1,
                              nullptr, d_vals));
+  XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
+  XF_CUDA_TRY(cudaMemcpyAsync(pctr_out, tr->pctr.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));
+  return tr->table->check_error();
+}
+
+// ---- the defined multi-view machine (XF_MODEL_MVM, step_mvm.cu): the batch with the tokens' field ids
+static int xf_upload_fields(xf_trainer* tr, XfBatchBuf& b, const uint8_t* fields, uint32_t nnz, const uint8_t** d_fields) {
+  *d_fields = nullptr;
+  if (!nnz) return XF_OK;
+  for (uint32_t j = 0; j < nnz; ++j)
+    if (fields[j] >= XF_MVM_FIELDS) { xf_set_error("field id %u of token %u: XF_MODEL_MVM takes field ids below %d", (unsigned)fields[j], j, XF_MVM_FIELDS); return XF_ERR_ARG; }
+  XF_TRY(b.fields.ensure((size_t)nnz));
+  XF_CUDA_TRY(cudaMemcpyAsync(b.fields.p, fields, (size_t)nnz, cudaMemcpyHostToDevice, tr->table->stream));
+  *d_fields = b.fields.as<uint8_t>();
+  return XF_OK;
+}
+
+XF_DLL int xf_trainer_step_host_fields(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* fields,
+                                       const float* vals, const uint8_t* labels, uint32_t rows, uint32_t nnz,
+                                       float* mean_abs_loss) {
+  if (!tr || !row_ptr || (!keys && nnz) || (!fields && nnz) || !labels) return XF_ERR_ARG;
+  if (tr->cfg.model != XF_MODEL_MVM) { xf_set_error("field ids need XF_MODEL_MVM"); return XF_ERR_ARG; }
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  if (rows == 0) { if (mean_abs_loss) *mean_abs_loss = 0.f; return XF_OK; }
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const int slot = (int)(tr->step_index & 1);
+  XfBatchBuf& b = tr->buf[slot];
+  ++tr->step_index;
+  XF_TRY(xf_upload_batch(tr, b, row_ptr, keys, labels, rows, nnz));
+  cudaStream_t st = tr->table->stream;
+  const float* d_vals = nullptr;
+  const uint8_t* d_fields = nullptr;
+  XF_TRY(xf_upload_vals(tr, b, vals, nnz, &d_vals));
+  XF_TRY(xf_upload_fields(tr, b, fields, nnz, &d_fields));
+  XF_CUDA_TRY(cudaMemsetAsync(tr->d_abs_loss + slot, 0, sizeof(float), st));
+  XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows, nnz, 0,
+                             tr->d_abs_loss + slot, d_vals, d_fields));
+  XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
+  ++tr->n_steps;
+  tr->n_rows += rows;
+  tr->n_nnz += nnz;
+  tr->last_rows = rows;
+  XF_CUDA_TRY(cudaMemcpyAsync(tr->h_abs_loss + slot, tr->d_abs_loss + slot, sizeof(float), cudaMemcpyDeviceToHost, st));
+  XF_CUDA_TRY(cudaStreamSynchronize(st));  // also: `fields` / `vals` may be reused by the caller
+  if (mean_abs_loss) *mean_abs_loss = tr->h_abs_loss[slot] / (float)rows;
+  return tr->table->check_error();
+}
+
+XF_DLL int xf_trainer_predict_host_fields(xf_trainer* tr, const uint32_t* row_ptr, const uint64_t* keys,
+                                          const uint8_t* fields, const float* vals, uint32_t rows, uint32_t nnz,
+                                          float* pctr_out) {
+  if (!tr || !row_ptr || (!keys && nnz) || (!fields && nnz) || !pctr_out) return XF_ERR_ARG;
+  if (tr->cfg.model != XF_MODEL_MVM) { xf_set_error("field ids need XF_MODEL_MVM"); return XF_ERR_ARG; }
+  XF_TRY(xf_check_batch(tr, rows, nnz));
+  if (rows == 0) return XF_OK;
+  XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+  const int slot = (int)(tr->step_index & 1);
+  XfBatchBuf& b = tr->buf[slot];
+  ++tr->step_index;
+  XF_TRY(xf_upload_batch(tr, b, row_ptr, keys, nullptr, rows, nnz));
+  cudaStream_t st = tr->table->stream;
+  XF_TRY(b.labels.ensure((size_t)rows + 1));
+  const float* d_vals = nullptr;
+  const uint8_t* d_fields = nullptr;
+  XF_TRY(xf_upload_vals(tr, b, vals, nnz, &d_vals));
+  XF_TRY(xf_upload_fields(tr, b, fields, nnz, &d_fields));
+  XF_TRY(xf_step_device_impl(tr, b.row_ptr.as<uint32_t>(), b.keys.as<uint64_t>(), b.labels.as<uint8_t>(), rows, nnz, 1,
+                             nullptr, d_vals, d_fields));
   XF_CUDA_TRY(cudaEventRecord(b.consumed, st));
   XF_CUDA_TRY(cudaMemcpyAsync(pctr_out, tr->pctr.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
   XF_CUDA_TRY(cudaStreamSynchronize(st));

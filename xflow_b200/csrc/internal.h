@@ -82,7 +82,7 @@ struct xf_table {
 };
 
 struct XfBatchBuf {
-  XfDevBuf row_ptr, keys, labels, ids, vals;
+  XfDevBuf row_ptr, keys, labels, ids, vals, fields;
   XfPinBuf h_row_ptr, h_keys, h_labels;
   cudaEvent_t copied = nullptr;   // H2D of this buffer finished (copy stream)
   cudaEvent_t consumed = nullptr; // kernels reading this buffer finished (compute stream)

@@ -68,6 +68,12 @@ void xf_launch_acc_tokens(const XfTableView& t, const uint32_t* slots, const uin
                           const uint32_t* meta_s, uint32_t cap, uint64_t work_bound, uint32_t* touched,
                           cudaStream_t st);
 
+// a defined multi-view machine on canonical tables (step_mvm.cu); field ids < XF_MVM_FIELDS, K <= 32
+#define XF_MVM_FIELDS 32
+void xf_launch_step_mvm(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys, const uint8_t* fields,
+                        const float* vals, const uint8_t* labels, int B, int mode, uint32_t* touched, float* loss_out,
+                        float* pctr_out, float* abs_loss_sum, cudaStream_t st);
+
 // canonical per-k FM with feature values (step_fmc.cu)
 void xf_launch_step_fmc(const XfTableView& t, const uint32_t* row_ptr, const uint64_t* keys, const float* vals,
                         const uint8_t* labels, int B, int mode, uint32_t* touched, float* loss_out, float* pctr_out,
