@@ -394,15 +394,20 @@ def run_workload(name, wl, args, rank, world, local, comm, api, torch, stream, s
     dom = max(kern, key=lambda k: k[2])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if world == 1 and os.path.exists(tpath):
+    if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(name, {}).get(dom[0].split(" ")[0])
+            import re
+            kname = re.search(r"xf_k_\w+", dom[0]).group(0)
+            traffic = json.load(open(tpath)).get(name, {}).get(kname)
         except Exception:
             traffic = None
     out["roofline"] = {
         "bound": "hbm", "kernel": dom[0], "achieved": dom[1] / dom[2] / 1e9 if dom[2] else None, "peak": peak, "unit": "GB/s",
         "frac": dom[1] / dom[2] / 1e9 / peak if dom[2] else None, "traffic": traffic,
-        "traffic_source": "ncu --set full capture of this workload (profiles/traffic.json)" if traffic else None,
+        "traffic_source": (("ncu --set full capture of this workload (profiles/traffic.json)" if world == 1 else
+                            "ncu --set full of the owner kernel with this workload's per-GPU token count on one GPU acting as "
+                            "its own peer (profiles/traffic.json, profiles/r02_multigpu.md); S launches together")
+                           if traffic else None),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1], "avg_launch_ms": dom[2] * 1e3,
         "kernels": [{"kernel": n, "algorithmic_bytes": b, "avg_ms": t * 1e3, "gbs": b / t / 1e9 if t else None} for n, b, t in kern],
         "step_algorithmic_bytes": b_step + b_update, "step_gbs": (b_step + b_update) / (ms * 1e-3 / steps) / 1e9,
