@@ -1,4 +1,4 @@
-"""CPU (gloo, world_size 2) model of the multi-GPU step's PROTOCOL (xflow_b200/csrc/comm.cu, mg_kernels.cu),
+"""CPU (gloo, world_size 2, 3 and 4) model of the multi-GPU step's PROTOCOL (xflow_b200/csrc/comm.cu, mg_kernels.cu),
 mirrored in Python over torch.distributed with the oracle's tables as the shards:
 
   worker  routes every TOKEN (key, row number) to the owner of its key            [xf_k_route]
@@ -25,7 +25,6 @@ from common import assert_close
 from oracle import oracle as O
 from xflow_b200 import api, datagen
 
-WORLD = 2
 ROUNDS = 3
 B, D, SPACE = 256, 12, 3000
 
@@ -36,6 +35,7 @@ def _batch(rank, rnd):
 
 def _exchange(arrs):
     """arrs[q] (numpy, any dtype/shape[0]) goes to rank q; returns the list received from each rank."""
+    WORLD = dist.get_world_size()
     out = [None] * WORLD
     gathered = [None] * WORLD
     dist.all_gather_object(gathered, [np.ascontiguousarray(a) for a in arrs])
@@ -54,7 +54,7 @@ def _seq_f32_sum(x, axis):
     return acc
 
 
-def _worker(rank, port, K, opt, ret):
+def _worker(rank, port, K, opt, WORLD, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
@@ -130,13 +130,14 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("K,opt", [(0, O.OPT_FTRL), (4, O.OPT_FTRL), (3, O.OPT_SGD)])
-def test_sharded_protocol_equals_lockstep_oracle(K, opt):
+@pytest.mark.parametrize("K,opt,WORLD", [(0, O.OPT_FTRL, 2), (4, O.OPT_FTRL, 2), (3, O.OPT_SGD, 2), (0, O.OPT_FTRL, 3),
+                                          (4, O.OPT_FTRL, 4)])
+def test_sharded_protocol_equals_lockstep_oracle(K, opt, WORLD):
     O.lib()
     api.lib()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(_free_port(), K, opt, ret), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(_free_port(), K, opt, WORLD, ret), nprocs=WORLD, join=True)
 
     # single-table lock-step schedule
     t = O.Table(K=K, opt=opt, init_mode=O.INIT_COUNTER, seed=9)
