@@ -143,3 +143,84 @@ def test_lazy_protocol_equals_eager_semantics_under_any_interleaving(seed):
     for k in a:
         assert tuple(x.tobytes() for x in a[k]) == tuple(x.tobytes() for x in eager[k]), k      # claim (2)
         assert tuple(x.tobytes() for x in a[k]) == tuple(x.tobytes() for x in b[k]), k          # claim (3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the sharded Push (mg_kernels.cu xf_k_push_tokens_lr): sources in rank order, every (round, source) pair its
+# own batch number, deposits made from the look at the row that the round's Pull stashed; a token whose CAS
+# fails either finds the row open for its own (round, source) -> integer add, or opened by an EARLIER source of
+# the round -> it continues from the words the failed CAS returned.
+# ---------------------------------------------------------------------------------------------------
+def run_sharded(rounds, rng):
+    t = LazyTable()
+    seq = 0
+    log = []
+    for sources in rounds:                                   # sources[s] = (rows_tokens, labels) of rank s
+        # Pull of the round, all sources: the stash is the raw row, the answer has the pending step applied
+        stash, resid = [], []
+        for rows_tokens, labels in sources:
+            st = [[t.snapshot(k) for k in toks] for toks in rows_tokens]
+            rs = []
+            for toks, snaps, y in zip(rows_tokens, st, labels):
+                wx = F(0)
+                for s_ in snaps:
+                    wx = F(wx + t.fold(s_, -1, t.rows_by_seq)[0])
+                rs.append(F(F(1.0 / (1.0 + np.exp(-np.float64(wx)))) - F(y)))
+            stash.append(st)
+            resid.append(rs)
+        log.append(resid)
+        # Push, sources in rank order; inside a source the tokens' atomic operations interleave at random
+        for s, (rows_tokens, labels) in enumerate(sources):
+            seq += 1
+            t.rows_by_seq[seq] = float(len(rows_tokens))
+            work = [(k, snap, int(np.rint(np.float64(resid[s][r]) * FIX)))
+                    for r, toks in enumerate(rows_tokens) for k, snap in zip(toks, stash[s][r])]
+            pend = [work[i] for i in rng.permutation(len(work))]
+            while pend:
+                i = int(rng.integers(0, len(pend)))
+                k, snap, fix = pend.pop(i)
+                cur = t.rows[k]
+                if tuple(cur) == snap:                       # CAS from the (possibly refreshed) look succeeds
+                    _, n, z = t.fold(snap, seq, t.rows_by_seq)
+                    t.rows[k] = [n, z, seq, fix]
+                elif cur[2] == seq:                          # open for this (round, source): integer add
+                    cur[3] += fix
+                else:                                        # an earlier source got there: retry from what came back
+                    assert cur[2] > snap[2] or snap[2] == 0
+                    pend.append((k, tuple(cur), fix))
+    return t.flushed(), log
+
+
+def run_sharded_eager(rounds, log):
+    state = {}
+    for sources, resid in zip(rounds, log):
+        for s, (rows_tokens, labels) in enumerate(sources):   # one step per (source, key), rank order
+            gsum = {}
+            for r, toks in enumerate(rows_tokens):
+                fix = int(np.rint(np.float64(resid[s][r]) * FIX))
+                for k in toks:
+                    gsum[k] = gsum.get(k, 0) + fix
+            for k, gfix in gsum.items():
+                w, n, z = state.get(k, (F(0), F(0), F(0)))
+                state[k] = ftrl_coord(grad_of(gfix, float(len(rows_tokens))), w, n, z)
+    return state
+
+
+@pytest.mark.parametrize("seed,S", [(1, 2), (2, 4), (3, 8)])
+def test_sharded_push_from_stale_looks_equals_rank_ordered_steps(seed, S):
+    rng = np.random.default_rng(seed)
+    rounds = []
+    for _ in range(4):
+        sources = []
+        for _s in range(S):
+            B = int(rng.integers(2, 10))
+            sources.append(([list(rng.zipf(1.5, int(rng.integers(0, 7))) % 23) for _ in range(B)], rng.integers(0, 2, B)))
+        rounds.append(sources)
+    a, log = run_sharded(rounds, np.random.default_rng(10 + seed))
+    b, _ = run_sharded(rounds, np.random.default_rng(20 + seed))
+    eager = run_sharded_eager(rounds, log)
+    touched = {k for sources in rounds for toks_l, _ in sources for toks in toks_l for k in toks}
+    assert set(a) == touched == set(eager)
+    for k in a:
+        assert tuple(x.tobytes() for x in a[k]) == tuple(x.tobytes() for x in eager[k]), k
+        assert tuple(x.tobytes() for x in a[k]) == tuple(x.tobytes() for x in b[k]), k
