@@ -1388,6 +1388,12 @@ XF_DLL int xf_trainer_set_profile(xf_trainer* tr, int on) {
   XF_CUDA_TRY(cudaStreamSynchronize(tr->table->stream));
   tr->profile = on != 0;
   tr->prof_used = 0;
+  if (tr->profile && tr->prof_events.empty()) {
+    // the first 256 steps' marks are created here, not inside the first profiled (and usually timed) step
+    XF_CUDA_TRY(cudaSetDevice(tr->table->cfg.device));
+    tr->prof_events.resize(4 * 256);
+    for (cudaEvent_t& e : tr->prof_events) XF_CUDA_TRY(cudaEventCreate(&e));
+  }
   return XF_OK;
 }
 
