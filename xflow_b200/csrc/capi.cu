@@ -163,6 +163,21 @@ int xf_table::next_seq() {
   return XF_OK;
 }
 
+// The sharded step takes S numbers per round and its pushes work from looks at the rows that were stashed BEFORE
+// the first of them: a restart in the middle of the round would leave stashed tags of the old numbering next to
+// batch numbers of the new one.  The restart is therefore taken before the round's Pull when fewer than n numbers
+// are left.
+int xf_table::reserve_seqs(int n) {
+  if (!view.lazy) return XF_OK;
+  if ((size_t)n + 2 > rows_cap) { xf_set_error("the batch-number ring (XFLOW_SEQ_RING = %zu) is too small for %d ranks", rows_cap, n); return XF_ERR_ARG; }
+  if ((size_t)seq + (size_t)n + 1 < rows_cap) return XF_OK;
+  xf_launch_flush_pending(view, stream);
+  ++launches;
+  XF_CUDA_TRY(cudaGetLastError());
+  seq = 0;
+  return XF_OK;
+}
+
 int xf_table::ensure_room(uint64_t incoming) {
   const uint64_t cap = view.mask + 1;
   // --- fast path: bound from the asynchronous read-backs, no host sync

@@ -483,6 +483,7 @@ int xf_mg_step(xf_trainer* tr, const uint32_t* d_row_ptr, const uint64_t* d_keys
   xf_launch_wait(flags + (size_t)XF_F_KEYS * XF_MG_MAX_SHARDS, S, step, t->d_error, mg->timeout_ns, st);
   if (step > 1) xf_launch_wait(flags + (size_t)XF_F_ROWV * XF_MG_MAX_SHARDS, S, step - 1, t->d_error, mg->timeout_ns, st);
   XF_MG_MARK(1);
+  if (mode == 0) XF_TRY(t->reserve_seqs(S));  // no restart of the batch numbering between this Pull and its pushes
   if (pm) XF_CUDA_TRY(cudaEventRecord(pm[0], st));
   xf_launch_pull_tokens(t->view, reinterpret_cast<const uint64_t*>(mg->slab + off_keys_p), meta_p, S, me, cap,
                         (uint64_t)nnz + 1, mg->peers, L.off_vals, mg->slots.as<uint32_t>(),

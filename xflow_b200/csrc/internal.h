@@ -70,6 +70,7 @@ struct xf_table {
   uint32_t* d_rows_by_seq = nullptr;
   size_t rows_cap = 0;
   int next_seq();            // advances seq; flushes all pending steps and restarts when the ring is used up
+  int reserve_seqs(int n);   // makes sure the next n numbers come without a restart (flushes now if they would not)
   // scratch for the host-pointer API (pull/push/import/export on host arrays); like KVWorker::Push/Pull
   // (kv_app.h:110-165) those entry points may be called from several threads: serialised by this mutex
   std::mutex host_mu;
